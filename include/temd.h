@@ -1,0 +1,109 @@
+/* libtemd — C ABI of the B200-native zonal-mean + TEM hot path (drop-in for jhollowed/PyTEMDiags).
+ *
+ * The reference is pure Python (no FFI); the entry points below are the operations its two public
+ * classes perform on the hot path, i.e. what a ctypes binding inside the reference would call
+ * (INTEGRATION.md shows that binding).  Reference citations are paths under PyTEMDiags/.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer (float64) unless the name ends in `_host`;
+ *   - field layout is [row][ncol] with row = time*nlev + lev ("[time][lev][ncol]", ncol contiguous),
+ *     leading dimension `ld` >= ncol in elements, `ld` even, base 16-byte aligned (TMA);
+ *   - coefficient blocks are [field][row][lpad], lpad = temd_plan_lpad() (L+1 rounded up to 8);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises
+ *     except temd_basis_build (one status read-back) and temd_check_finite;
+ *   - return value 0 = ok, < 0 = argument / numerical error, > 0 = cudaError_t;
+ *     temd_last_error() returns a thread-local description.
+ *   - inputs are borrowed read-only; the plan owns only its basis and split-K workspace.
+ */
+#ifndef TEMD_H
+#define TEMD_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct temd_plan temd_plan;
+
+int temd_version(void);
+const char* temd_last_error(void);
+
+/* sph_zonal_averager.__init__ (sph_zonal_mean.py:36-181): ncol = N native columns, L = max degree,
+ * nlat_out = M output latitudes. */
+int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_plan** plan);
+int temd_plan_destroy(temd_plan* plan);
+int temd_plan_lpad(const temd_plan* plan);
+
+/* sph_zonal_averager.sph_compute_matrices (sph_zonal_mean.py:302-422): builds the Legendre basis at
+ * x = cos(colatitude) of the native (x[N]) and output (x_out[M]) latitudes by three-term recurrence
+ * (replaces sph_harm loops :359-370), the Gram matrix, its Cholesky factor, and the orthonormalised
+ * basis that replaces Y0inv = lstsq(Y0, I) (:389).  Fails (<0) if Y0 is numerically rank-deficient.
+ * sanity[0] = sum diag(Y0inv*Y0), sanity[1] = sum offdiag (the reference's logged check :393-398),
+ * written to host memory if sanity_host != NULL. */
+int temd_basis_build(temd_plan* plan, const double* x, const double* x_out, double* sanity_host, void* stream);
+
+/* Dense exports of the reference's attributes Y0 [N][L+1], Y0inv [L+1][N], Y0p [M][L+1]
+ * (sph_zonal_mean.py:420-422); any pointer may be NULL. */
+int temd_basis_export(temd_plan* plan, double* Y0, double* Y0inv, double* Y0p, void* stream);
+
+/* Forward projection, first GEMM of sph_zonal_mean.py:251: coef[f][row][:] = Q^T fields[f][row][:].
+ * fields_host: host array of nfields device pointers.  If lev_scale != NULL, rows of field
+ * `scale_field` are multiplied by lev_scale[row % nlev] (theta = T*(p0/p)^k, tem_diagnostics.py:498). */
+int temd_project(temd_plan* plan, const double* const* fields_host, int nfields, int rows, size_t ld,
+                 const double* lev_scale, int scale_field, int nlev, double* coef, void* stream);
+
+/* sph_zonal_mean (sph_zonal_mean.py:291-296): out[row][m] on the output latitudes, ld_out >= M, even. */
+int temd_synth_out(temd_plan* plan, const double* coef, int rows, double* out, size_t ld_out, void* stream);
+
+/* sph_zonal_mean_native (sph_zonal_mean.py:285-290): out[row][n] on the native columns. */
+int temd_synth_native(temd_plan* plan, const double* coef, int rows, double* out, size_t ld_out, void* stream);
+
+/* _decompose_zm_eddy + _compute_fluxes (tem_diagnostics.py:510-558), fused: per column tile forms the
+ * native zonal means of u, v, T, omega from coef4 ([4][rows][lpad], order u,v,T,omega, T unscaled),
+ * the eddies, the products u'v', u'omega', v'T' and projects them: coef_flux [3][rows][lpad]
+ * (order upvp, upwapp, vptp).  coef4's theta block holds theta coefficients (already scaled) and the
+ * kernel forms theta = lev_scale[row % nlev] * T on the fly.  Eddies and products never reach HBM. */
+int temd_eddy_flux_project(temd_plan* plan, const double* u, const double* v, const double* t, const double* w,
+                           int rows, size_t ld, const double* coef4, const double* lev_scale, int nlev,
+                           double* coef_flux, void* stream);
+
+/* _compute_derivatives + the ten diagnostics methods (tem_diagnostics.py:574-797; tem_util.py:57-243).
+ * zm: 7 zonal-mean arrays [nt][nlev][M] in the order ub, vb, thetab, wapb, upvpb, upwappb, vptpb.
+ * gp/gl: np.gradient coefficient triplets (a,b,c) per level [3][nlev] / per latitude [3][M].
+ * out: TEMD_NOUT arrays [nt][nlev][M] in the order of TEMD_OUT_* below (+2 scratch planes). */
+typedef struct temd_epilogue_args {
+    int nt, nlev, nlat;
+    size_t ld;              /* leading dimension (>= nlat) of every [nt*nlev][ld] plane */
+    const double* zm;       /* [7][nt*nlev][ld] */
+    const double* p;        /* [nlev] Pa */
+    const double* latr;     /* [nlat] radians */
+    const double* gp;       /* [3][nlev] interior np.gradient coefficients a, b, c */
+    const double* gl;       /* [3][nlat] */
+    int p_uniform, lat_uniform;   /* NumPy's exactly-uniform-spacing branch (then hp / hlat is the spacing) */
+    double hp, hlat;
+    const double* coslat;   /* [nlat] */
+    const double* f;        /* [nlat] Coriolis parameter */
+    double p0, a, H, g0, pi;
+    double* out;            /* [TEMD_NOUT + 2][nt*nlev][ld]; the last two planes are scratch */
+} temd_epilogue_args;
+
+enum {
+    TEMD_OUT_DUB_DP = 0, TEMD_OUT_DTHETAB_DP, TEMD_OUT_UBCOSLAT, TEMD_OUT_DUBCOSLAT_DLAT, TEMD_OUT_PSI,
+    TEMD_OUT_PSICOSLAT, TEMD_OUT_DPSICOSLAT_DLAT, TEMD_OUT_DPSI_DP, TEMD_OUT_INT_VBDP,
+    TEMD_OUT_VTEM, TEMD_OUT_OMEGATEM, TEMD_OUT_WTEM, TEMD_OUT_PSITEM, TEMD_OUT_EPFY, TEMD_OUT_EPFZ,
+    TEMD_OUT_EPDIV, TEMD_OUT_UTENDEPFD, TEMD_OUT_UTENDVTEM, TEMD_OUT_UTENDWTEM, TEMD_NOUT
+};
+
+int temd_tem_epilogue(temd_plan* plan, const temd_epilogue_args* args, void* stream);
+
+/* NaN screen of sph_zonal_mean.py:219-221 done on the small coefficient block (NaNs in a field
+ * propagate into its coefficients): returns 0 if all n values are finite, -2 otherwise (synchronises). */
+int temd_check_finite(const double* data, size_t n, void* stream);
+
+/* Synthetic benchmark/test fields: out[t][lev][ncol], field 0..4 = ua, va, ta, wap, q. */
+int temd_synth_fields(double* out, int field, int seed, int t0, int nt, int nlev, int ncol, size_t ld,
+                      const double* lat_rad, const double* lon_rad, const double* plev_hpa, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -20,7 +20,7 @@ TEM_INTERMEDIATES = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb', 
                      'dthetab_dp', 'ubcoslat', 'dubcoslat_dlat', 'psi', 'psicoslat',
                      'dpsicoslat_dlat', 'dpsi_dp', 'int_vbdp')
 
-_trapz = getattr(np, 'trapz', None) or np.trapezoid
+_trapz = getattr(np, 'trapezoid', None) or np.trapz   # same function; np.trapz (tem_util.py:232) is its deprecated alias
 
 # scipy.special.sph_harm_y(l, 0, ., 0) returns NaN for l >= 646
 _SCIPY_LMAX = 645

@@ -1,0 +1,380 @@
+// extern "C" entry points of libtemd (declared in include/temd.h) + plan management.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/temd.h"
+#include "temd_common.cuh"
+#include "temd_internal.h"
+
+namespace temd {
+
+static thread_local char g_err[512] = "";
+
+int temd_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TEMD_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return temd_set_error((int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                  __FILE__, __LINE__);                                               \
+    } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_tma_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
+                uint32_t box0, uint32_t box1) {
+    PFN_encodeTiled enc = get_encode();
+    if (enc == nullptr) return temd_set_error(-3, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15))
+        return temd_set_error(-1, "TMA operand must be 16-byte aligned with a 16-byte-multiple row stride "
+                                  "(base %p, stride %llu B): use an even leading dimension",
+                              base, (unsigned long long)row_stride_bytes);
+    if (box0 * sizeof(double) > 128 || box1 > 256) return temd_set_error(-1, "TMA box too large");
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstr[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return temd_set_error(-3, "cuTensorMapEncodeTiled failed (CUresult %d; dims %llu x %llu, stride %llu, box %u x %u)",
+                              (int)r, (unsigned long long)dim0, (unsigned long long)dim1,
+                              (unsigned long long)row_stride_bytes, box0, box1);
+    return 0;
+}
+
+__global__ void k_check_finite(const double* __restrict__ d, size_t n, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i < n; i += stride) bad |= !isfinite(d[i]);
+    if (bad) *flag = 1;
+}
+
+__global__ void k_trace_offdiag(const double* __restrict__ G, int n, int ld, double* __restrict__ out2) {
+    // single block: out2[0] = trace, out2[1] = sum of off-diagonal entries
+    __shared__ double s_tr[256], s_off[256];
+    double tr = 0.0, off = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        const double v = G[(size_t)i * ld + j];
+        if (i == j) tr += v; else off += v;
+    }
+    s_tr[threadIdx.x] = tr; s_off[threadIdx.x] = off;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { s_tr[threadIdx.x] += s_tr[threadIdx.x + w]; s_off[threadIdx.x] += s_off[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = s_tr[0]; out2[1] = s_off[0]; }
+}
+
+// out[i][j] = in[j][i]; in is [rows_in][ld_in], out is [cols_in][ld_out]  (dense exports only)
+__global__ void k_transpose(const double* __restrict__ in, int rows_in, int cols_in, size_t ld_in,
+                            double* __restrict__ out, size_t ld_out) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int rr = r0 + r, cc = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (rr < rows_in && cc < cols_in) ? in[(size_t)rr * ld_in + cc] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int oc = r0 + threadIdx.x, orow = c0 + r;
+        if (orow < cols_in && oc < rows_in) out[(size_t)orow * ld_out + oc] = tile[threadIdx.x][r];
+    }
+}
+
+}  // namespace temd
+
+using namespace temd;
+
+struct temd_plan {
+    int dev, N, L, Lp, lpad, M, sms;
+    size_t ld_q, ld_p;
+    double *qt, *qt_alt;     // whitened basis Q^T [lpad][ld_q] and ping-pong buffer
+    double *qpt, *qpt_alt;   // whitened output-grid basis [lpad][ld_p]
+    double *linv, *linv1, *linv2, *gram, *lt;   // [lpad][lpad] each
+    double *rec_a, *rec_b;   // recurrence coefficients [L+1]
+    double *x, *x_out;       // copies of the node coordinates (for exports)
+    double *work;            // split-K partials
+    size_t work_doubles;
+    int* status;
+    double* sanity;
+    bool built;
+};
+
+static int ensure_work(temd_plan* p, size_t doubles) {
+    if (doubles <= p->work_doubles) return 0;
+    if (p->work) TEMD_CUDA(cudaFree(p->work));
+    p->work = nullptr;
+    p->work_doubles = 0;
+    TEMD_CUDA(cudaMalloc(&p->work, doubles * sizeof(double)));
+    p->work_doubles = doubles;
+    return 0;
+}
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+extern "C" int temd_version(void) { return 100; }
+extern "C" const char* temd_last_error(void) { return g_err; }
+
+extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_plan** out) {
+    if (out == nullptr) return temd_set_error(-1, "plan_create: null output");
+    *out = nullptr;
+    if (ncol < 1 || L < 0 || nlat_out < 1) return temd_set_error(-1, "plan_create: bad sizes (ncol %d, L %d, M %d)", ncol, L, nlat_out);
+    if (L + 1 > 1024) return temd_set_error(-1, "plan_create: L = %d exceeds the supported maximum 1023", L);
+    if (L + 1 > ncol) return temd_set_error(-1, "plan_create: L+1 = %d exceeds ncol = %d (Y0 would be rank-deficient)", L + 1, ncol);
+    TEMD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TEMD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return temd_set_error(-4, "libtemd is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    temd_plan* p = new temd_plan();
+    memset(p, 0, sizeof(*p));
+    p->dev = device; p->N = ncol; p->L = L; p->Lp = L + 1; p->M = nlat_out;
+    p->lpad = (int)round_up(L + 1, 8);
+    p->sms = prop.multiProcessorCount;
+    p->ld_q = round_up(ncol, 16);
+    p->ld_p = round_up(nlat_out, 16);
+    const size_t lp = p->lpad;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](double** ptr, size_t n) { if (e == cudaSuccess) e = cudaMalloc(ptr, n * sizeof(double)); };
+    alloc(&p->qt, lp * p->ld_q); alloc(&p->qt_alt, lp * p->ld_q);
+    alloc(&p->qpt, lp * p->ld_p); alloc(&p->qpt_alt, lp * p->ld_p);
+    alloc(&p->linv, lp * lp); alloc(&p->linv1, lp * lp); alloc(&p->linv2, lp * lp); alloc(&p->gram, lp * lp); alloc(&p->lt, lp * lp);
+    alloc(&p->rec_a, lp); alloc(&p->rec_b, lp);
+    alloc(&p->x, ncol); alloc(&p->x_out, nlat_out);
+    alloc(&p->sanity, 2);
+    if (e == cudaSuccess) e = cudaMalloc(&p->status, sizeof(int));
+    if (e != cudaSuccess) {
+        temd_plan_destroy(p);
+        return temd_set_error((int)e, "plan_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" int temd_plan_destroy(temd_plan* p) {
+    if (p == nullptr) return 0;
+    cudaSetDevice(p->dev);
+    double* bufs[] = {p->qt, p->qt_alt, p->qpt, p->qpt_alt, p->linv, p->linv1, p->linv2, p->gram, p->lt,
+                      p->rec_a, p->rec_b, p->x, p->x_out, p->work, p->sanity};
+    for (double* b : bufs) if (b) cudaFree(b);
+    if (p->status) cudaFree(p->status);
+    delete p;
+    return 0;
+}
+
+extern "C" int temd_plan_lpad(const temd_plan* p) { return p ? p->lpad : -1; }
+
+static int gram_of(temd_plan* p, const double* basis, cudaStream_t st) {
+    int ntb, lblocks;
+    project_lblocks(p->lpad, &ntb, &lblocks);
+    const int tiles = (p->Lp + 127) / 128;
+    const int nchunks = (p->N + 15) / 16;
+    const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 512);
+    int rc = ensure_work(p, project_workspace_doubles(1, p->Lp, p->lpad, nsplit));
+    if (rc) return rc;
+    const double* xs[1] = {basis};
+    return launch_project(xs, 1, p->Lp, p->N, p->ld_q, basis, p->lpad, p->ld_q, p->gram, p->work, nsplit, nullptr, -1, 1, st);
+}
+
+extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_out, double* sanity_host, void* stream) {
+    if (p == nullptr || x == nullptr || x_out == nullptr) return temd_set_error(-1, "basis_build: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    // recurrence coefficients: Y_l = a_l x Y_{l-1} - b_l Y_{l-2}
+    std::vector<double> ra(p->lpad, 0.0), rb(p->lpad, 0.0);
+    const double PI = 3.141592653589793238462643383279502884;
+    ra[0] = std::sqrt(1.0 / (4.0 * PI));
+    if (p->L >= 1) ra[1] = std::sqrt(3.0 / (4.0 * PI));
+    for (int l = 2; l <= p->L; l++) {
+        ra[l] = std::sqrt(4.0 * l * l - 1.0) / l;
+        rb[l] = ((l - 1.0) / l) * std::sqrt((2.0 * l + 1.0) / (2.0 * l - 3.0));
+    }
+    TEMD_CUDA(cudaMemcpyAsync(p->rec_a, ra.data(), p->lpad * sizeof(double), cudaMemcpyHostToDevice, st));
+    TEMD_CUDA(cudaMemcpyAsync(p->rec_b, rb.data(), p->lpad * sizeof(double), cudaMemcpyHostToDevice, st));
+    TEMD_CUDA(cudaStreamSynchronize(st));   // ra/rb are stack-owned
+    TEMD_CUDA(cudaMemcpyAsync(p->x, x, p->N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TEMD_CUDA(cudaMemcpyAsync(p->x_out, x_out, p->M * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc;
+    // K1: raw basis (transposed) on both grids
+    if ((rc = launch_basis(p->x, p->N, p->L, p->rec_a, p->rec_b, p->qt_alt, p->ld_q, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+    if ((rc = launch_basis(p->x_out, p->M, p->L, p->rec_a, p->rec_b, p->qpt_alt, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+    // CholeskyQR pass 1: G = Y0^T Y0 = L1 L1^T,  Q1 = Y0 L1^-T
+    if ((rc = gram_of(p, p->qt_alt, st))) return rc;
+    if ((rc = launch_chol_inv(p->gram, p->lpad, p->Lp, p->lt, p->linv1, p->lpad, p->lpad, p->status, st))) return temd_set_error(rc, "cholesky launch failed");
+    int status = 0;
+    TEMD_CUDA(cudaMemcpyAsync(&status, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TEMD_CUDA(cudaStreamSynchronize(st));
+    if (status != 0)
+        return temd_set_error(-5, "basis_build: Y0 is numerically rank-deficient (Cholesky pivot %d of %d non-positive); "
+                                  "L = %d is too large for this grid", status - 1, p->Lp, p->L);
+    if ((rc = launch_synth(p->linv1, p->lpad, p->lpad, p->lpad, p->qt_alt, p->N, p->ld_q, p->qt, p->ld_q, st))) return rc;
+    if ((rc = launch_synth(p->linv1, p->lpad, p->lpad, p->lpad, p->qpt_alt, p->M, p->ld_p, p->qpt, p->ld_p, st))) return rc;
+    // pass 2 (CholeskyQR2): G2 = Q1^T Q1 = L2 L2^T,  Q = Q1 L2^-T;  L^-1 = L2^-1 L1^-1
+    if ((rc = gram_of(p, p->qt, st))) return rc;
+    if ((rc = launch_chol_inv(p->gram, p->lpad, p->Lp, p->lt, p->linv2, p->lpad, p->lpad, p->status, st))) return temd_set_error(rc, "cholesky launch failed");
+    TEMD_CUDA(cudaMemcpyAsync(&status, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TEMD_CUDA(cudaStreamSynchronize(st));
+    if (status != 0) return temd_set_error(-5, "basis_build: second Cholesky pass failed at pivot %d", status - 1);
+    if ((rc = launch_synth(p->linv2, p->lpad, p->lpad, p->lpad, p->qt, p->N, p->ld_q, p->qt_alt, p->ld_q, st))) return rc;
+    if ((rc = launch_synth(p->linv2, p->lpad, p->lpad, p->lpad, p->qpt, p->M, p->ld_p, p->qpt_alt, p->ld_p, st))) return rc;
+    std::swap(p->qt, p->qt_alt);
+    std::swap(p->qpt, p->qpt_alt);
+    if ((rc = launch_matmul_small(p->linv2, p->linv1, p->linv, p->lpad, p->lpad, st))) return temd_set_error(rc, "matmul launch failed");
+    if (sanity_host != nullptr) {
+        // reference's logged check (sph_zonal_mean.py:393-398): Y0inv Y0 = L^-T (Q^T Q) L^T; we report Q^T Q
+        if ((rc = gram_of(p, p->qt, st))) return rc;
+        k_trace_offdiag<<<1, 256, 0, st>>>(p->gram, p->Lp, p->lpad, p->sanity);
+        TEMD_CUDA(cudaGetLastError());
+        TEMD_CUDA(cudaMemcpyAsync(sanity_host, p->sanity, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    TEMD_CUDA(cudaStreamSynchronize(st));
+    p->built = true;
+    return 0;
+}
+
+extern "C" int temd_basis_export(temd_plan* p, double* Y0, double* Y0inv, double* Y0p, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "basis_export: basis not built");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    int rc;
+    dim3 tb(32, 8);
+    if (Y0 != nullptr) {
+        if ((rc = launch_basis(p->x, p->N, p->L, p->rec_a, p->rec_b, p->qt_alt, p->ld_q, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+        dim3 grid((p->N + 31) / 32, (p->Lp + 31) / 32);
+        k_transpose<<<grid, tb, 0, st>>>(p->qt_alt, p->Lp, p->N, p->ld_q, Y0, p->Lp);
+    }
+    if (Y0p != nullptr) {
+        if ((rc = launch_basis(p->x_out, p->M, p->L, p->rec_a, p->rec_b, p->qpt_alt, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+        dim3 grid((p->M + 31) / 32, (p->Lp + 31) / 32);
+        k_transpose<<<grid, tb, 0, st>>>(p->qpt_alt, p->Lp, p->M, p->ld_p, Y0p, p->Lp);
+    }
+    if (Y0inv != nullptr) {
+        // Y0inv = L^-T Q^T : rows l of (Linv^T)[l][l'] = Linv[l'][l]
+        dim3 grid((p->lpad + 31) / 32, (p->lpad + 31) / 32);
+        k_transpose<<<grid, tb, 0, st>>>(p->linv, p->lpad, p->lpad, p->lpad, p->lt, p->lpad);
+        if ((rc = launch_synth(p->lt, p->Lp, p->lpad, p->lpad, p->qt, p->N, p->ld_q, p->qt_alt, p->ld_q, st))) return rc;
+        TEMD_CUDA(cudaMemcpy2DAsync(Y0inv, (size_t)p->N * sizeof(double), p->qt_alt, p->ld_q * sizeof(double),
+                                    (size_t)p->N * sizeof(double), p->Lp, cudaMemcpyDeviceToDevice, st));
+    }
+    TEMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int temd_project(temd_plan* p, const double* const* fields_host, int nfields, int rows, size_t ld,
+                            const double* lev_scale, int scale_field, int nlev, double* coef, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "project: basis not built (call temd_basis_build)");
+    if (fields_host == nullptr || coef == nullptr || rows < 1 || nfields < 1 || nfields > TEMD_MAX_FIELDS || ld < (size_t)p->N)
+        return temd_set_error(-1, "project: bad arguments (nfields %d, rows %d, ld %zu, ncol %d)", nfields, rows, ld, p->N);
+    if (lev_scale != nullptr && nlev < 1) return temd_set_error(-1, "project: nlev must be >= 1 with lev_scale");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    int ntb, lblocks;
+    project_lblocks(p->lpad, &ntb, &lblocks);
+    const int tiles = ((rows + 127) / 128) * nfields;
+    const int nchunks = (p->N + 15) / 16;
+    const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 64);
+    int rc = ensure_work(p, project_workspace_doubles(nfields, rows, p->lpad, nsplit));
+    if (rc) return rc;
+    return launch_project(fields_host, nfields, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef, p->work, nsplit,
+                          lev_scale, scale_field, nlev < 1 ? 1 : nlev, st);
+}
+
+extern "C" int temd_synth_out(temd_plan* p, const double* coef, int rows, double* out, size_t ld_out, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "synth_out: basis not built");
+    if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->M) return temd_set_error(-1, "synth_out: bad arguments");
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    return launch_synth(coef, rows, p->lpad, p->lpad, p->qpt, p->M, p->ld_p, out, ld_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int temd_synth_native(temd_plan* p, const double* coef, int rows, double* out, size_t ld_out, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "synth_native: basis not built");
+    if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->N) return temd_set_error(-1, "synth_native: bad arguments");
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    return launch_synth(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int temd_check_finite(const double* data, size_t n, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int* flag = nullptr;
+    TEMD_CUDA(cudaMalloc(&flag, sizeof(int)));
+    cudaMemsetAsync(flag, 0, sizeof(int), st);
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 1184);
+    k_check_finite<<<blocks ? blocks : 1, 256, 0, st>>>(data, n, flag);
+    int h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(flag);
+    if (e != cudaSuccess) return temd_set_error((int)e, "check_finite: %s", cudaGetErrorString(e));
+    if (h) return temd_set_error(-2, "non-finite values (NaN/Inf) found");
+    return 0;
+}
+
+namespace temd { struct EpilogueArgs { temd_epilogue_args a; }; }
+
+extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const double* v, const double* t, const double* w,
+                                      int rows, size_t ld, const double* coef4, const double* lev_scale, int nlev,
+                                      double* coef_flux, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "eddy_flux_project: basis not built");
+    if (!u || !v || !t || !w || !coef4 || !coef_flux || rows < 1 || ld < (size_t)p->N)
+        return temd_set_error(-1, "eddy_flux_project: bad arguments");
+    if (!eddy_supported(p->lpad)) return temd_set_error(-1, "eddy_flux_project: L = %d too large for the fused kernel (max 407)", p->L);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    const int nchunks = (p->N + 15) / 16;
+    const int nsplit = eddy_pick_split(rows, p->lpad, nchunks, p->sms);
+    int rc = ensure_work(p, eddy_workspace_doubles(rows, p->lpad, nsplit));
+    if (rc) return rc;
+    const double* x4[4] = {u, v, t, w};
+    return launch_eddy_flux_project(x4, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef4, coef_flux, p->work, nsplit,
+                                    lev_scale, nlev, st);
+}
+
+extern "C" int temd_tem_epilogue(temd_plan* p, const temd_epilogue_args* args, void* stream) {
+    if (p == nullptr || args == nullptr) return temd_set_error(-1, "tem_epilogue: null argument");
+    if (args->nlev < 2 || args->nlat < 2 || args->nt < 1 || args->ld < (size_t)args->nlat)
+        return temd_set_error(-1, "tem_epilogue: need nlev >= 2, nlat >= 2, nt >= 1 (np.gradient needs two points)");
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    EpilogueArgs w;
+    w.a = *args;
+    int rc = launch_tem_epilogue(w, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return temd_set_error(rc, "tem_epilogue: kernel launch failed");
+    return 0;
+}
+
+extern "C" int temd_synth_fields(double* out, int field, int seed, int t0, int nt, int nlev, int ncol, size_t ld,
+                                 const double* lat_rad, const double* lon_rad, const double* plev_hpa, void* stream) {
+    if (!out || !lat_rad || !lon_rad || !plev_hpa || field < 0 || field > 4 || nt < 1 || nlev < 1 || ncol < 1 || ld < (size_t)ncol)
+        return temd_set_error(-1, "synth_fields: bad arguments");
+    int rc = launch_synth_fields(out, field, seed, t0, nt, nlev, ncol, ld, lat_rad, lon_rad, plev_hpa,
+                                 reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return temd_set_error(rc, "synth_fields: kernel launch failed");
+    return 0;
+}

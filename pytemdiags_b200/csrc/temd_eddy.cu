@@ -1,0 +1,318 @@
+// K5 `eddy_flux_project`: fused native-grid synthesis -> eddies -> flux products -> projection.
+//
+// Replaces, in one pass over the four input fields (reference PyTEMDiags/tem_diagnostics.py):
+//   _decompose_zm_eddy  :517-529   X' = X - ZM.sph_zonal_mean_native(X)   (X = ua, va, theta, wap)
+//   _compute_fluxes     :547-557   upvp = up*vp, upwapp = up*wapp, vptp = vp*thetap  and the first
+//                                  GEMM of their zonal means (sph_zonal_mean.py:251)
+// The reference materialises 4 native means, 4 eddies and 3 products (11 N x K x T arrays); here
+// none of them reaches HBM.  Per CTA: BM (time,lev) rows, a split-K range of 16-column chunks.
+//
+//   per chunk:  GEMM1  S_f[BM x 16] = C_f[BM x lpad] * QT[lpad x 16]      f = u, v, theta, omega
+//               E_f = X_f - S_f   (theta: X = lev_scale * T), written in place over the X tile
+//               GEMM2  acc_g[BM x lpad] += (E_a .* E_b)[BM x 16] * QT^T[16 x lpad]   g = uv, uw, v.theta
+//
+// Both GEMMs are DMMA.8x8x4; the QT chunk tile ([lpad rows][16 cols], TMA, 128-B swizzle) is the
+// B operand of both: "MN-major" (contraction over tile rows) in GEMM1, "K-major" in GEMM2.
+// C_f lives in shared memory for the CTA's lifetime (row-major, row stride = 4 or 12 mod 16
+// doubles so that the GEMM1 A fragments are bank-conflict-free under the mnmajor_k permutation).
+#include "temd_common.cuh"
+#include "temd_internal.h"
+
+namespace temd {
+
+constexpr int ED_WARPS = 8;
+constexpr int ED_THREADS = (ED_WARPS + 1) * 32;
+constexpr int ED_SMEM_LIMIT = 232448 - 2048;   // 227 KB minus alignment slack and static barriers
+constexpr int ED_MAX_STAGES = 4;
+
+struct EddyMaps {
+    CUtensorMap x[4];   // dims {N, rows}, box {16, BM}
+    CUtensorMap q;      // dims {N, lpad}, box {16, min(lpad, 256)}
+};
+
+struct EddyParams {
+    int rows, nchunks, chunks_per_split, nsplit;
+    int nt;            // lpad / 8
+    int ls;            // Cs row stride (doubles)
+    int stages;
+    int nlev;
+    int qbox;          // rows per QT TMA box (divides lpad, <= 256)
+    const double* coef4;      // [4][rows][lpad]
+    const double* lev_scale;  // [nlev] or null
+    double* part;             // [nsplit][3][rows][lpad]
+};
+
+__host__ __device__ inline int eddy_ls(int lpad) {
+    int ls = lpad;
+    while ((ls & 15) != 4 && (ls & 15) != 12) ls++;
+    return ls;
+}
+
+template <int BM, int NJ>
+__global__ void __launch_bounds__(ED_THREADS, 1)
+k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
+    constexpr int MT = BM / 8;          // m8-tiles per CTA
+    constexpr int NW2 = ED_WARPS / MT;  // warps sharing one m-tile in GEMM2
+    constexpr int NF1 = (MT == 4) ? 2 : 1;   // GEMM1: fields per warp
+    constexpr int NN1 = (MT == 1) ? 1 : 2;   // GEMM1: n8-tiles (of the 16-column chunk) per warp
+    constexpr int XF_BYTES = BM * TILE_ROW_BYTES;   // one field's X tile
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bars[2 * ED_MAX_STAGES];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lpad = p.nt * 8;
+    const int stage_bytes = 4 * XF_BYTES + p.nt * 8 * TILE_ROW_BYTES;
+    const int ntiles = (p.rows + BM - 1) / BM;
+    const int tile = blockIdx.x % ntiles;
+    const int split = blockIdx.x / ntiles;
+    const int row0 = tile * BM;
+    const int c_begin = split * p.chunks_per_split;
+    const int c_end = min(c_begin + p.chunks_per_split, p.nchunks);
+    const int nloc = c_end - c_begin;
+    const int STAGES = p.stages;
+
+    const uint32_t smem_base = smem_u32(smem), bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (ED_MAX_STAGES + s); };
+    double* Cs = reinterpret_cast<double*>(smem + (size_t)STAGES * stage_bytes);
+    const uint32_t cs_base = smem_base + STAGES * stage_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), ED_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == ED_WARPS) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            for (int f = 0; f < 4; f++) tma_prefetch_desc(&maps.x[f]);
+            tma_prefetch_desc(&maps.q);
+            for (int i = 0; i < nloc; i++) {
+                const int s = i % STAGES;
+                mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+                const uint32_t dst = smem_base + s * stage_bytes;
+                const int col = (c_begin + i) * TILE_K;
+#pragma unroll
+                for (int f = 0; f < 4; f++) tma_load_2d(dst + f * XF_BYTES, &maps.x[f], col, row0, full_bar(s));
+                for (int r = 0; r < lpad; r += p.qbox)
+                    tma_load_2d(dst + 4 * XF_BYTES + r * TILE_ROW_BYTES, &maps.q, col, r, full_bar(s));
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ consumers ------------------------------
+    const int g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x;   // 0..255
+    // spectral coefficients of the 4 fields for this CTA's rows -> Cs[f][r][LS]
+    {
+        const int total = 4 * BM * lpad;
+        for (int e = tid; e < total; e += ED_WARPS * 32) {
+            const int l = e % lpad;
+            const int r = (e / lpad) % BM;
+            const int f = e / (lpad * BM);
+            const int row = row0 + r;
+            Cs[(size_t)(f * BM + r) * p.ls + l] = (row < p.rows) ? p.coef4[((size_t)f * p.rows + row) * lpad + l] : 0.0;
+        }
+    }
+    named_bar_sync(1, ED_WARPS * 32);
+
+    // GEMM1 roles
+    int mi1, f1, jn1;
+    if (MT == 4) { mi1 = warp & 3; f1 = (warp >> 2) * 2; jn1 = 0; }
+    else if (MT == 2) { mi1 = warp & 1; f1 = warp >> 1; jn1 = 0; }
+    else { mi1 = 0; f1 = warp >> 1; jn1 = warp & 1; }
+    // GEMM2 roles
+    const int mi2 = warp % MT;
+    const int wq = warp / MT;
+    const int j_begin = (wq * p.nt) / NW2;
+    const int j_end = ((wq + 1) * p.nt) / NW2;
+
+    // theta scale for this thread's GEMM1 row (field 2 only)
+    double tscale = 1.0;
+    {
+        const int row = row0 + mi1 * 8 + g;
+        if (p.lev_scale != nullptr && row < p.rows) tscale = p.lev_scale[row % p.nlev];
+    }
+
+    double acc[3][NJ][2];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) acc[a][j][0] = acc[a][j][1] = 0.0;
+
+    // per-thread constant offsets
+    const int k1c0 = mnmajor_k(t, 0), k1c1 = mnmajor_k(t, 1);
+    uint32_t a1_off[NF1];   // GEMM1 A: Cs[(f*BM + mi1*8 + g)][.]
+#pragma unroll
+    for (int ff = 0; ff < NF1; ff++) a1_off[ff] = cs_base + (uint32_t)(((f1 + ff) * BM + mi1 * 8 + g) * p.ls) * 8u;
+    uint32_t coff2[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) coff2[kk] = kmajor_col_off(g, t, kk);
+    const uint32_t e_row_off = (uint32_t)((mi2 * 8 + g) * TILE_ROW_BYTES);
+    const uint32_t q_off = 4 * XF_BYTES;
+
+    for (int i = 0; i < nloc; i++) {
+        const int s = i % STAGES;
+        mbar_wait(full_bar(s), (i / STAGES) & 1);
+        const uint32_t st = smem_base + s * stage_bytes;
+        const uint32_t qs = st + q_off;
+
+        // ---------------- GEMM1: S = C * QT (contraction over l = QT tile rows) ----------------
+        double sacc[NF1][NN1][2];
+#pragma unroll
+        for (int ff = 0; ff < NF1; ff++)
+#pragma unroll
+            for (int nn = 0; nn < NN1; nn++) sacc[ff][nn][0] = sacc[ff][nn][1] = 0.0;
+#pragma unroll 2
+        for (int l8 = 0; l8 < p.nt; l8++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int kin = c ? k1c1 : k1c0;           // row inside the 8-row group
+                const int k = l8 * 8 + kin;
+                double a[NF1], b[NN1];
+#pragma unroll
+                for (int ff = 0; ff < NF1; ff++) a[ff] = lds64(a1_off[ff] + (uint32_t)k * 8u);
+#pragma unroll
+                for (int nn = 0; nn < NN1; nn++) {
+                    const int jn = jn1 + nn;
+                    b[nn] = lds64(qs + (uint32_t)k * TILE_ROW_BYTES + (uint32_t)((((jn * 4 + (g >> 1)) ^ kin) & 7) << 4) + (uint32_t)((g & 1) << 3));
+                }
+#pragma unroll
+                for (int ff = 0; ff < NF1; ff++)
+#pragma unroll
+                    for (int nn = 0; nn < NN1; nn++) dmma(sacc[ff][nn][0], sacc[ff][nn][1], a[ff], b[nn]);
+            }
+        }
+        // ---------------- eddies, in place over the X tiles ----------------
+#pragma unroll
+        for (int ff = 0; ff < NF1; ff++) {
+            const int f = f1 + ff;
+            const double sc = (f == 2) ? tscale : 1.0;
+#pragma unroll
+            for (int nn = 0; nn < NN1; nn++) {
+                const int row = mi1 * 8 + g;
+                const int col = (jn1 + nn) * 8 + 2 * t;
+                const uint32_t addr = st + f * XF_BYTES + swz_off(row, col);
+                const double2 x = lds128(addr);
+                sts128(addr, sc * x.x - sacc[ff][nn][0], sc * x.y - sacc[ff][nn][1]);
+            }
+        }
+        named_bar_sync(1, ED_WARPS * 32);
+
+        // ---------------- GEMM2: acc += (E_a .* E_b) * QT^T (contraction over the 16 columns) ----------------
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const uint32_t eo = st + e_row_off + coff2[kk];
+            const double eu = lds64(eo);
+            const double ev = lds64(eo + XF_BYTES);
+            const double et = lds64(eo + 2 * XF_BYTES);
+            const double ew = lds64(eo + 3 * XF_BYTES);
+            const double a_uv = eu * ev, a_uw = eu * ew, a_vt = ev * et;
+            const uint32_t bo = qs + (uint32_t)(g * TILE_ROW_BYTES) + coff2[kk];
+#pragma unroll
+            for (int jj = 0; jj < NJ; jj++) {
+                const int j = j_begin + jj;
+                if (j < j_end) {
+                    const double b = lds64(bo + (uint32_t)j * 8u * TILE_ROW_BYTES);
+                    dmma(acc[0][jj][0], acc[0][jj][1], a_uv, b);
+                    dmma(acc[1][jj][0], acc[1][jj][1], a_uw, b);
+                    dmma(acc[2][jj][0], acc[2][jj][1], a_vt, b);
+                }
+            }
+        }
+        // the E tiles were written through the generic proxy; order them before the next TMA refill
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+    }
+
+    // ------------------------------ split-K partials ------------------------------
+    const int row = row0 + mi2 * 8 + g;
+    if (row < p.rows) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            double* out = p.part + (((size_t)split * 3 + a) * p.rows + row) * lpad;
+#pragma unroll
+            for (int jj = 0; jj < NJ; jj++) {
+                const int j = j_begin + jj;
+                if (j < j_end) *reinterpret_cast<double2*>(out + j * 8 + 2 * t) = make_double2(acc[a][jj][0], acc[a][jj][1]);
+            }
+        }
+    }
+}
+
+static int eddy_bm(int nt) { return nt <= 13 ? 32 : (nt <= 26 ? 16 : 8); }
+
+int eddy_supported(int lpad) { return lpad >= 8 && lpad / 8 <= 51; }
+
+static int eddy_stages(int nt, int bm, int* smem_bytes) {
+    const int lpad = nt * 8;
+    const int cs_bytes = 4 * bm * eddy_ls(lpad) * 8;
+    const int stage_bytes = 4 * bm * TILE_ROW_BYTES + lpad * TILE_ROW_BYTES;
+    int stages = (ED_SMEM_LIMIT - cs_bytes) / stage_bytes;
+    if (stages > ED_MAX_STAGES) stages = ED_MAX_STAGES;
+    *smem_bytes = stages * stage_bytes + cs_bytes + 1024;
+    return stages;
+}
+
+int eddy_pick_split(int rows, int lpad, int nchunks, int sms) {
+    const int bm = eddy_bm(lpad / 8);
+    return project_pick_split((rows + bm - 1) / bm, nchunks, sms, 64);
+}
+
+size_t eddy_workspace_doubles(int rows, int lpad, int nsplit) { return (size_t)nsplit * 3 * rows * lpad; }
+
+template <int BM, int NJ>
+static int launch_eddy_t(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int ntiles = (p.rows + BM - 1) / BM;
+    k_eddy<BM, NJ><<<ntiles * p.nsplit, ED_THREADS, smem, stream>>>(maps, p);
+    return (int)cudaGetLastError();
+}
+
+int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t ld_x, const double* qt, int lpad,
+                             size_t ld_q, const double* coef4, double* coef_flux, double* part, int nsplit,
+                             const double* lev_scale, int nlev, cudaStream_t stream) {
+    if (!eddy_supported(lpad)) return temd_set_error(-1, "eddy_flux_project: L+1 > 408 is not supported by the fused kernel");
+    const int nt = lpad / 8;
+    const int bm = eddy_bm(nt);
+    EddyMaps maps;
+    int rc;
+    for (int f = 0; f < 4; f++)
+        if ((rc = make_tma_2d(&maps.x[f], x4[f], (uint64_t)ncol, (uint64_t)rows, ld_x * sizeof(double), TILE_K, bm))) return rc;
+    int qd = 1;   // largest divisor d of nt with 8 d <= 256
+    for (int d = 1; d <= 32 && d <= nt; d++) if (nt % d == 0) qd = d;
+    if ((rc = make_tma_2d(&maps.q, qt, (uint64_t)ncol, (uint64_t)lpad, ld_q * sizeof(double), TILE_K, qd * 8))) return rc;
+    EddyParams p;
+    p.qbox = qd * 8;
+    p.rows = rows;
+    p.nchunks = (ncol + TILE_K - 1) / TILE_K;
+    p.nsplit = nsplit;
+    p.chunks_per_split = (p.nchunks + nsplit - 1) / nsplit;
+    p.nt = nt;
+    p.ls = eddy_ls(lpad);
+    p.nlev = nlev < 1 ? 1 : nlev;
+    p.coef4 = coef4;
+    p.lev_scale = lev_scale;
+    p.part = part;
+    int smem;
+    p.stages = eddy_stages(nt, bm, &smem);
+    if (p.stages < 2) return temd_set_error(-1, "eddy_flux_project: not enough shared memory for lpad = %d", lpad);
+    const int nw2 = ED_WARPS / (bm / 8);
+    const int nj = (nt + nw2 - 1) / nw2;
+    rc = -1;
+#define ED_CASE(BM_, NJ_) if (bm == BM_ && nj == NJ_) rc = launch_eddy_t<BM_, NJ_>(maps, p, smem, stream);
+#define ED_CASES(BM_) ED_CASE(BM_, 1) ED_CASE(BM_, 2) ED_CASE(BM_, 3) ED_CASE(BM_, 4) ED_CASE(BM_, 5) ED_CASE(BM_, 6) ED_CASE(BM_, 7)
+    ED_CASES(32) ED_CASES(16) ED_CASES(8)
+#undef ED_CASES
+#undef ED_CASE
+    if (rc) return temd_set_error(rc, "eddy_flux_project: kernel launch failed (bm %d, nj %d)", bm, nj);
+    return launch_reduce_partials(part, coef_flux, nsplit, 3, rows, lpad, nullptr, -1, 1, stream);
+}
+
+}  // namespace temd

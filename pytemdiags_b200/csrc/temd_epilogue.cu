@@ -1,0 +1,172 @@
+// K6 `tem_epilogue`: every stencil / scan / closed-form diagnostic on the (time, lev, lat) zonal means.
+//
+// Replaces reference PyTEMDiags/tem_diagnostics.py `_compute_derivatives` (:574-599) and the methods
+// vtem (:622), omegatem (:639), wtem (:657), psitem (:674), epfy (:691-692), epfz (:709-710),
+// epdiv (:730-736), utendepfd (:753), utendvtem (:771-773), utendwtem (:790-791), and the helpers in
+// PyTEMDiags/tem_util.py: multiply_lat (:80), multiply_p (:117), lat_gradient (:154),
+// p_gradient (:192), p_integral (:230-232).  Arrays are [time][lev][lat] (lat contiguous, leading
+// dimension ld) and tiny (2.5 MB each at config 1): three L2-resident passes, HBM/L2-bound.
+//
+// np.gradient semantics (edge_order=1): one-sided first differences at the two ends; interior is
+// a*f[i-1] + b*f[i] + c*f[i+1] with the non-uniform second-order coefficients, or
+// (f[i+1]-f[i-1])/(2h) when NumPy detects an exactly uniform coordinate.
+#include "../../include/temd.h"
+#include "temd_common.cuh"
+#include "temd_internal.h"
+
+namespace temd {
+
+struct Axis {
+    const double* x;      // coordinate [n]
+    const double* coef;   // [3][n] interior coefficients a, b, c
+    int n;
+    int uniform;
+    double h;
+};
+
+__device__ __forceinline__ double grad3(const Axis& ax, int i, double fm, double f0, double fp) {
+    if (i == 0) return ax.uniform ? (fp - f0) / ax.h : (fp - f0) / (ax.x[1] - ax.x[0]);
+    if (i == ax.n - 1) return ax.uniform ? (f0 - fm) / ax.h : (f0 - fm) / (ax.x[ax.n - 1] - ax.x[ax.n - 2]);
+    if (ax.uniform) return (fp - fm) / (2.0 * ax.h);
+    return ax.coef[i] * fm + ax.coef[ax.n + i] * f0 + ax.coef[2 * ax.n + i] * fp;
+}
+
+struct EpiDev {
+    int nt, nlev, nlat;
+    size_t ld, plane;     // plane = nt*nlev*ld
+    const double* zm;
+    double* out;
+    const double* p;
+    const double* coslat;
+    const double* f;
+    Axis ap, al;
+    double p0, a, H, g0, pi;
+};
+
+#define ZM(q) (e.zm + (size_t)(q) * e.plane)
+#define OUT(q) (e.out + (size_t)(q) * e.plane)
+enum { Z_UB = 0, Z_VB, Z_THETAB, Z_WAPB, Z_UPVPB, Z_UPWAPPB, Z_VPTPB };
+enum { S_FPHICOS = TEMD_NOUT, S_FP = TEMD_NOUT + 1 };
+
+__device__ __forceinline__ bool epi_index(const EpiDev& e, int& t, int& k, int& m, size_t& idx) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)e.nt * e.nlev * e.nlat;
+    if (gid >= total) return false;
+    m = (int)(gid % e.nlat);
+    k = (int)((gid / e.nlat) % e.nlev);
+    t = (int)(gid / ((size_t)e.nlat * e.nlev));
+    idx = ((size_t)t * e.nlev + k) * e.ld + m;
+    return true;
+}
+
+// pass A: dub_dp, dthetab_dp, psi, ubcoslat, dubcoslat_dlat, psicoslat   (tem_diagnostics.py:579-592)
+__global__ void k_epi_a(const EpiDev e) {
+    int t, k, m; size_t idx;
+    if (!epi_index(e, t, k, m, idx)) return;
+    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
+    const double* ub = ZM(Z_UB);
+    const double* th = ZM(Z_THETAB);
+    const double dub_dp = grad3(e.ap, k, ub[up], ub[idx], ub[dn]);
+    const double dth_dp = grad3(e.ap, k, th[up], th[idx], th[dn]);
+    const double psi = ZM(Z_VPTPB)[idx] / dth_dp;                                     // :590
+    const double c0 = e.coslat[m];
+    const double ubc = ub[idx] * c0;                                                  // :584
+    const double ubc_m = (m > 0) ? ub[idx - 1] * e.coslat[m - 1] : ubc;
+    const double ubc_p = (m < e.nlat - 1) ? ub[idx + 1] * e.coslat[m + 1] : ubc;
+    OUT(TEMD_OUT_DUB_DP)[idx] = dub_dp;
+    OUT(TEMD_OUT_DTHETAB_DP)[idx] = dth_dp;
+    OUT(TEMD_OUT_PSI)[idx] = psi;
+    OUT(TEMD_OUT_UBCOSLAT)[idx] = ubc;
+    OUT(TEMD_OUT_DUBCOSLAT_DLAT)[idx] = grad3(e.al, m, ubc_m, ubc, ubc_p);            // :586
+    OUT(TEMD_OUT_PSICOSLAT)[idx] = psi * c0;                                          // :592
+}
+
+// int_vbdp (tem_util.py:230-232): cumulative trapezoid from the model top, one thread per (t, lat)
+__global__ void k_epi_scan(const EpiDev e) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)e.nt * e.nlat) return;
+    const int m = (int)(gid % e.nlat), t = (int)(gid / e.nlat);
+    const double* vb = ZM(Z_VB);
+    double* o = OUT(TEMD_OUT_INT_VBDP);
+    size_t idx = (size_t)t * e.nlev * e.ld + m;
+    double acc = 0.0, prev = vb[idx];
+    o[idx] = 0.0;
+    for (int k = 1; k < e.nlev; k++) {
+        idx += e.ld;
+        const double cur = vb[idx];
+        acc += (e.p[k] - e.p[k - 1]) * (cur + prev) / 2.0;
+        o[idx] = acc;
+        prev = cur;
+    }
+}
+
+// pass B: everything that needs psi / psicoslat neighbours   (tem_diagnostics.py:594-597, 615-716, 763-797)
+__global__ void k_epi_b(const EpiDev e) {
+    int t, k, m; size_t idx;
+    if (!epi_index(e, t, k, m, idx)) return;
+    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
+    const size_t lm = (m > 0) ? idx - 1 : idx, lp = (m < e.nlat - 1) ? idx + 1 : idx;
+    const double* psi_a = OUT(TEMD_OUT_PSI);
+    const double* psic_a = OUT(TEMD_OUT_PSICOSLAT);
+    const double psi = psi_a[idx];
+    const double dpsi_dp = grad3(e.ap, k, psi_a[up], psi, psi_a[dn]);                 // :596
+    const double dpsic_dlat = grad3(e.al, m, psic_a[lm], psic_a[idx], psic_a[lp]);    // :594
+    const double c0 = e.coslat[m], pk = e.p[k];
+    const double acos = e.a * c0, iacos = 1.0 / (e.a * c0);
+    const double dub_dp = OUT(TEMD_OUT_DUB_DP)[idx];
+    const double vtem = ZM(Z_VB)[idx] - dpsi_dp;                                      // :622
+    const double omegatem = ZM(Z_WAPB)[idx] + dpsic_dlat * iacos;                     // :639
+    const double wtem = omegatem * (-e.H / pk);                                       // :657
+    const double psitem = 2 * e.pi * e.a / e.g0 * ((OUT(TEMD_OUT_INT_VBDP)[idx] - psi) * c0);   // :674
+    const double epfy = ((dub_dp * psi - ZM(Z_UPVPB)[idx]) * acos) * (pk / e.p0);     // :691-692
+    const double xz = e.f[m] - OUT(TEMD_OUT_DUBCOSLAT_DLAT)[idx] * iacos;             // :709
+    const double epfz = -e.H / e.p0 * ((xz * psi - ZM(Z_UPWAPPB)[idx]) * acos);       // :710
+    OUT(TEMD_OUT_DPSI_DP)[idx] = dpsi_dp;
+    OUT(TEMD_OUT_DPSICOSLAT_DLAT)[idx] = dpsic_dlat;
+    OUT(TEMD_OUT_VTEM)[idx] = vtem;
+    OUT(TEMD_OUT_OMEGATEM)[idx] = omegatem;
+    OUT(TEMD_OUT_WTEM)[idx] = wtem;
+    OUT(TEMD_OUT_PSITEM)[idx] = psitem;
+    OUT(TEMD_OUT_EPFY)[idx] = epfy;
+    OUT(TEMD_OUT_EPFZ)[idx] = epfz;
+    OUT(TEMD_OUT_UTENDVTEM)[idx] = vtem * xz;                                         // :771-773
+    OUT(TEMD_OUT_UTENDWTEM)[idx] = -omegatem * dub_dp;                                // :790-791
+    OUT(S_FPHICOS)[idx] = (epfy * (e.p0 / pk)) * c0;                                  // :730, :733
+    OUT(S_FP)[idx] = epfz * -e.p0 / e.H;                                              // :731
+}
+
+// pass C: epdiv, utendepfd   (tem_diagnostics.py:734-736, 753)
+__global__ void k_epi_c(const EpiDev e) {
+    int t, k, m; size_t idx;
+    if (!epi_index(e, t, k, m, idx)) return;
+    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
+    const size_t lm = (m > 0) ? idx - 1 : idx, lp = (m < e.nlat - 1) ? idx + 1 : idx;
+    const double* fc = OUT(S_FPHICOS);
+    const double* fp = OUT(S_FP);
+    const double iacos = 1.0 / (e.a * e.coslat[m]);
+    const double epdiv = grad3(e.al, m, fc[lm], fc[idx], fc[lp]) * iacos + grad3(e.ap, k, fp[up], fp[idx], fp[dn]);
+    OUT(TEMD_OUT_EPDIV)[idx] = epdiv;
+    OUT(TEMD_OUT_UTENDEPFD)[idx] = epdiv * iacos;
+}
+
+struct EpilogueArgs { temd_epilogue_args a; };
+
+int launch_tem_epilogue(const EpilogueArgs& wrap, cudaStream_t stream) {
+    const temd_epilogue_args& a = wrap.a;
+    EpiDev e;
+    e.nt = a.nt; e.nlev = a.nlev; e.nlat = a.nlat; e.ld = a.ld;
+    e.plane = (size_t)a.nt * a.nlev * a.ld;
+    e.zm = a.zm; e.out = a.out; e.p = a.p; e.coslat = a.coslat; e.f = a.f;
+    e.ap = Axis{a.p, a.gp, a.nlev, a.p_uniform, a.hp};
+    e.al = Axis{a.latr, a.gl, a.nlat, a.lat_uniform, a.hlat};
+    e.p0 = a.p0; e.a = a.a; e.H = a.H; e.g0 = a.g0; e.pi = a.pi;
+    const size_t total = (size_t)a.nt * a.nlev * a.nlat;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    k_epi_a<<<blocks, 256, 0, stream>>>(e);
+    k_epi_scan<<<(unsigned)(((size_t)a.nt * a.nlat + 127) / 128), 128, 0, stream>>>(e);
+    k_epi_b<<<blocks, 256, 0, stream>>>(e);
+    k_epi_c<<<blocks, 256, 0, stream>>>(e);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace temd

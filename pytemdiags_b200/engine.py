@@ -1,0 +1,190 @@
+"""Thin host-side driver over libtemd: owns a `temd_plan`, hands torch device tensors to the C ABI.
+
+PyTorch is used for device memory and streams only; every numerical operation on the hot path is a
+libtemd kernel launch.  No CPU fallback: constructing an Engine without the library or without a
+CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import P0, H, a, g0, pi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def gradient_coefficients(x):
+    """Interior coefficients of `np.gradient(f, x)` (NumPy's second-order non-uniform stencil) and its
+    uniform-spacing branch flag, reproducing numpy/lib/function_base.py::gradient.
+
+    Returns (coef[3][n] float64, uniform: bool, h: float).
+    """
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    coef = np.zeros((3, n))
+    dx = np.diff(x)
+    uniform = bool((dx == dx[0]).all())
+    if n > 2:
+        dx1, dx2 = dx[:-1], dx[1:]
+        coef[0, 1:-1] = -(dx2) / (dx1 * (dx1 + dx2))
+        coef[1, 1:-1] = (dx2 - dx1) / (dx1 * dx2)
+        coef[2, 1:-1] = dx1 / (dx2 * (dx1 + dx2))
+    return coef, uniform, float(dx[0])
+
+
+class Engine:
+    """One zonal-averaging plan (native grid, output grid, truncation L) on one GPU."""
+
+    def __init__(self, lat, lat_out, L, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('pytemdiags_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lat = np.ascontiguousarray(np.asarray(lat, dtype=np.float64))
+        self.lat_out = np.ascontiguousarray(np.asarray(lat_out, dtype=np.float64))
+        self.N, self.M, self.L = int(self.lat.shape[0]), int(self.lat_out.shape[0]), int(L)
+        self.Mld = self.M + (self.M & 1)
+        self._plan = C.c_void_p(0)
+        _lib.check(self.lib.temd_plan_create(self.device.index or 0, self.N, self.L, self.M, C.byref(self._plan)),
+                   'temd_plan_create')
+        self.lpad = self.lib.temd_plan_lpad(self._plan)
+        self.built = False
+        self.sanity = None
+
+    def __del__(self):
+        try:
+            if getattr(self, '_plan', None) and self._plan.value:
+                self.lib.temd_plan_destroy(self._plan)
+                self._plan = C.c_void_p(0)
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, arr):
+        return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+
+    # ---- sph_compute_matrices (sph_zonal_mean.py:302-422) ----
+    def build_basis(self, sanity=False):
+        # x = cos(colatitude), computed exactly like the reference: coalt = deg2rad(90 - lat)
+        x = self._dev(np.cos(np.deg2rad(90 - self.lat)))
+        x_out = self._dev(np.cos(np.deg2rad(90 - self.lat_out)))
+        san = (C.c_double * 2)()
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_basis_build(self._plan, _ptr(x), _ptr(x_out), san if sanity else None, self.stream)
+        _lib.check(rc, 'temd_basis_build')
+        self.built = True
+        if sanity:
+            self.sanity = (san[0], san[1])
+        return self
+
+    def export_matrices(self, Y0=True, Y0inv=True, Y0p=True):
+        """Dense Y0 (N,L+1), Y0inv (L+1,N), Y0p (M,L+1) as device tensors (reference attributes)."""
+        Lp = self.L + 1
+        o0 = torch.empty((self.N, Lp), dtype=torch.float64, device=self.device) if Y0 else None
+        oi = torch.empty((Lp, self.N), dtype=torch.float64, device=self.device) if Y0inv else None
+        op = torch.empty((self.M, Lp), dtype=torch.float64, device=self.device) if Y0p else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_basis_export(self._plan, _ptr(o0), _ptr(oi), _ptr(op), self.stream)
+        _lib.check(rc, 'temd_basis_export')
+        return o0, oi, op
+
+    # ---- zonal-mean pieces ----
+    def _check_field(self, x):
+        if not (x.is_cuda and x.dtype == torch.float64 and x.dim() == 2 and x.shape[1] == self.N
+                and x.stride(1) == 1 and x.stride(0) % 2 == 0 and x.data_ptr() % 16 == 0):
+            raise RuntimeError('field must be a float64 CUDA tensor [rows][ncol], ncol contiguous, even row stride, '
+                               '16-byte aligned')
+
+    def project(self, fields, lev_scale=None, scale_field=-1, nlev=1):
+        """coef[f][row][lpad] = Q^T fields[f][row][:]  (fields: list of [rows][N] device tensors)."""
+        rows, ld = fields[0].shape[0], fields[0].stride(0)
+        for x in fields:
+            self._check_field(x)
+            if x.shape[0] != rows or x.stride(0) != ld:
+                raise RuntimeError('all fields must share shape and stride')
+        coef = torch.empty((len(fields), rows, self.lpad), dtype=torch.float64, device=self.device)
+        ptrs = (C.c_void_p * len(fields))(*[x.data_ptr() for x in fields])
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_project(self._plan, ptrs, len(fields), rows, ld, _ptr(lev_scale), scale_field, nlev,
+                                       _ptr(coef), self.stream)
+        _lib.check(rc, 'temd_project')
+        return coef
+
+    def synth_out(self, coef):
+        """[.., rows, lpad] -> zonal means on the output latitudes [.., rows, M] (view of an Mld-strided buffer)."""
+        c2 = coef.reshape(-1, self.lpad)
+        out = torch.empty((c2.shape[0], self.Mld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_synth_out(self._plan, _ptr(c2), c2.shape[0], _ptr(out), self.Mld, self.stream)
+        _lib.check(rc, 'temd_synth_out')
+        return out.reshape(tuple(coef.shape[:-1]) + (self.Mld,))[..., :self.M]
+
+    def synth_native(self, coef, out=None):
+        c2 = coef.reshape(-1, self.lpad)
+        ld = self.N + (self.N & 1)
+        if out is None:
+            out = torch.empty((c2.shape[0], ld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_synth_native(self._plan, _ptr(c2), c2.shape[0], _ptr(out), out.stride(0), self.stream)
+        _lib.check(rc, 'temd_synth_native')
+        return out[:, :self.N]
+
+    def check_finite(self, t, what='input'):
+        rc = self.lib.temd_check_finite(_ptr(t), t.numel(), self.stream)
+        if rc == -2:
+            # same failure the reference raises at sph_zonal_mean.py:219-221
+            raise RuntimeError('Variable {} has nans! Spectral zonal averager cannot handle nans; '
+                               'please replace or remove them'.format(what))
+        _lib.check(rc, 'temd_check_finite')
+
+    def eddy_flux_project(self, u, v, t, w, coef4, lev_scale, nlev):
+        for x in (u, v, t, w):
+            self._check_field(x)
+        rows, ld = u.shape[0], u.stride(0)
+        out = torch.empty((3, rows, self.lpad), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_eddy_flux_project(self._plan, _ptr(u), _ptr(v), _ptr(t), _ptr(w), rows, ld, _ptr(coef4),
+                                                 _ptr(lev_scale), nlev, _ptr(out), self.stream)
+        _lib.check(rc, 'temd_eddy_flux_project')
+        return out
+
+    def tem_epilogue(self, zm, p_pa, f, coslat, p0=P0):
+        """zm: [7][nt][nlev][Mld-strided M] device tensor (as returned by synth_out on a [7][nt*nlev][lpad]
+        coefficient block).  Returns dict name -> [nt][nlev][M] device tensors."""
+        nt, nlev = zm.shape[1], zm.shape[2]
+        assert zm.shape[0] == 7 and zm.shape[3] == self.M and zm.stride(2) == self.Mld and zm.stride(3) == 1
+        latr = np.deg2rad(self.lat_out)
+        gp, p_uni, hp = gradient_coefficients(p_pa)
+        gl, l_uni, hl = gradient_coefficients(latr)
+        d = dict(p=self._dev(p_pa), latr=self._dev(latr), gp=self._dev(gp), gl=self._dev(gl),
+                 coslat=self._dev(coslat), f=self._dev(f))
+        nout = len(_lib.EPILOGUE_OUTPUTS)
+        out = torch.empty((nout + 2, nt, nlev, self.Mld), dtype=torch.float64, device=self.device)
+        args = _lib.EpilogueArgs(nt=nt, nlev=nlev, nlat=self.M, ld=self.Mld, zm=zm.data_ptr(), p=d['p'].data_ptr(),
+                                 latr=d['latr'].data_ptr(), gp=d['gp'].data_ptr(), gl=d['gl'].data_ptr(),
+                                 p_uniform=int(p_uni), lat_uniform=int(l_uni), hp=hp, hlat=hl,
+                                 coslat=d['coslat'].data_ptr(), f=d['f'].data_ptr(),
+                                 p0=float(p0), a=a, H=H, g0=g0, pi=pi, out=out.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_tem_epilogue(self._plan, C.byref(args), self.stream)
+        _lib.check(rc, 'temd_tem_epilogue')
+        self._keepalive = d
+        return {name: out[i, :, :, :self.M] for i, name in enumerate(_lib.EPILOGUE_OUTPUTS)}
+
+    def synth_fields(self, field, seed, t0, nt, plev_hpa, lat_rad_dev, lon_rad_dev, plev_dev, out=None):
+        nlev = plev_dev.shape[0]
+        ld = self.N + (self.N & 1)
+        if out is None:
+            out = torch.empty((nt * nlev, ld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_synth_fields(_ptr(out), field, seed, t0, nt, nlev, self.N, out.stride(0),
+                                            _ptr(lat_rad_dev), _ptr(lon_rad_dev), _ptr(plev_dev), self.stream)
+        _lib.check(rc, 'temd_synth_fields')
+        return out[:, :self.N]

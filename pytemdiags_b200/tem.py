@@ -1,0 +1,394 @@
+"""`TEMDiagnostics` — host-side mirror of reference PyTEMDiags/tem_diagnostics.py:31-797.
+
+Same constructor (both call shapes), the same public methods, properties and error
+behaviour.  The heavy lifting (zonal means, eddy fluxes, stencils) happens once in the constructor,
+as in the reference (`__init__` :239-259), but on the GPU through libtemd; the methods return the
+cached results of the fused epilogue instead of recomputing them.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import arrays as ar
+from . import constants as const
+from .constants import P0
+from .zonal import sph_zonal_averager
+
+DEFAULT_DIMS = {'horz': 'ncol', 'vert': 'plev', 'time': 'time'}   # tem_diagnostics.py:25
+
+_ARG_ORDER = ('lat_native', 'q', 'p0', 'zm_dlat', 'L', 'dim_names', 'grid_name', 'zm_grid_name',
+              'map_save_dest', 'overwrite_map', 'zm_pole_points', 'debug_level', 'logfile')
+_DEFAULTS = dict(lat_native=None, q=None, p0=P0, zm_dlat=1, L=50, dim_names=DEFAULT_DIMS, grid_name=None,
+                 zm_grid_name=None, map_save_dest=None, overwrite_map=False, zm_pole_points=False,
+                 debug_level=1, logfile=None)
+_ZM_NAMES = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb')
+_METHODS = ('vtem', 'omegatem', 'wtem', 'psitem', 'epfy', 'epfz', 'epdiv', 'utendepfd', 'utendvtem', 'utendwtem')
+_DERIVED = ('dub_dp', 'dthetab_dp', 'ubcoslat', 'dubcoslat_dlat', 'psi', 'psicoslat', 'dpsicoslat_dlat',
+            'dpsi_dp', 'int_vbdp')
+
+
+def _is_1d_of_len(x, n):
+    try:
+        r = ar.raw(x)
+        return r.ndim == 1 and r.shape[0] == n
+    except Exception:
+        return False
+
+
+class TEMDiagnostics:
+    def __init__(self, ua, va, ta, wap, *args, **kwargs):
+        '''
+        TEM diagnostics on a pressure vertical coordinate (Gerber & Manzini 2016, Table A1).
+
+        Call shapes (both accepted):
+          TEMDiagnostics(ua, va, ta, wap, lat_native, q=None, p0=P0, zm_dlat=1, L=50, dim_names=...,
+                         grid_name=None, zm_grid_name=None, map_save_dest=None, overwrite_map=False,
+                         zm_pole_points=False, debug_level=1, logfile=None)   # tem_diagnostics.py:32-36
+          TEMDiagnostics(ua, va, ta, wap, p, lat, ...)                        # README.md:40
+
+        ua, va, ta, wap : DataArray-like (dims in any order, vertical coordinate = pressure in hPa),
+            or numpy arrays / torch tensors together with `dims=` (default: the reference's internal
+            order ('ncol', 'plev', 'time')) and `p=`.
+        p : 1-D pressure levels (hPa unless p_units='Pa') or a gridpoint pressure field in Pa that is
+            constant on each level (pressure-level data).  Mandatory for raw arrays.
+        Extra keywords of this build: dims, p, p_units, time, device, slab_bytes.
+        '''
+        opts = dict(_DEFAULTS)
+        extra = {k: kwargs.pop(k) for k in ('dims', 'p', 'p_units', 'time', 'device', 'slab_bytes', 'lat')
+                 if k in kwargs}
+        pos = list(args)
+        ncol_guess = None
+        # README shape: (p, lat, ...) -- the 6th positional is a 1-D latitude vector
+        if len(pos) >= 2 and not isinstance(pos[1], (list, tuple)) and pos[1] is not None \
+                and hasattr(ar.raw(pos[1]), 'ndim') and ar.raw(pos[1]).ndim == 1 and ar.raw(pos[0]).ndim >= 1 \
+                and 'lat' not in extra and 'lat_native' not in kwargs:
+            ncol_guess = ar.raw(pos[1]).shape[0]
+            if not _is_1d_of_len(pos[0], ncol_guess) or ar.raw(pos[0]).ndim > 1:
+                extra['p'] = pos.pop(0)
+        elif 'lat' in extra and len(pos) >= 1 and 'lat_native' not in kwargs:
+            extra['p'] = pos.pop(0)
+        if len(pos) > len(_ARG_ORDER):
+            raise TypeError('too many positional arguments')
+        for name, val in zip(_ARG_ORDER, pos):
+            opts[name] = val
+        for k_, v_ in kwargs.items():
+            if k_ not in opts:
+                raise TypeError("__init__() got an unexpected keyword argument '{}'".format(k_))
+            opts[k_] = v_
+        if 'lat' in extra:
+            opts['lat_native'] = extra['lat']
+        if opts['lat_native'] is None:
+            raise TypeError("missing required argument 'lat_native' (latitudes of the native columns)")
+
+        # ---- get input args (tem_diagnostics.py:217-236)
+        self.ua, self.va, self.ta, self.wap = ua, va, ta, wap
+        self.p0 = opts['p0']
+        self.q = opts['q']
+        self.ntrac = None
+        self.lat_native = opts['lat_native']
+        self.L = opts['L']
+        self.zm_dlat = opts['zm_dlat']
+        self.dim_names = opts['dim_names']
+        self.zm_pole_points = opts['zm_pole_points']
+        self.grid_name = opts['grid_name']
+        self.zm_grid_name = opts['zm_grid_name']
+        self.map_save_dest = opts['map_save_dest']
+        self.overwrite_map = opts['overwrite_map']
+        self.debug_level = opts['debug_level']
+        self.logfile = opts['logfile']
+        self._dims_in = extra.get('dims')
+        self._p_in = extra.get('p')
+        self._p_units = extra.get('p_units')
+        self._time_in = extra.get('time')
+        self._device = extra.get('device')
+        self._slab_bytes = extra.get('slab_bytes')
+
+        self._config_dims()
+
+        # ---- zonal averaging object (tem_diagnostics.py:243-249)
+        self.ZM = sph_zonal_averager(self._lat_native_np, self._lat_zm, self.L, grid_name=self.grid_name,
+                                     grid_out_name=self.zm_grid_name, save_dest=self.map_save_dest,
+                                     debug=self.debug_level > 1, overwrite=self.overwrite_map,
+                                     ncoldim=self.ncolname, device=self._device)
+        self.ZM.sph_compute_matrices(overwrite=self.overwrite_map)
+        self._zonal_mean = self.ZM.sph_zonal_mean
+
+        self._compute_all()
+        self._out_file = None
+
+    # ------------------------------------------------------------------
+    def _log(self, s):
+        if self.debug_level > 0:
+            if self.logfile is not None:
+                with open(self.logfile, 'a') as f:
+                    f.write('(PyTEMDiags debug) {}\n'.format(s))
+            else:
+                print('(PyTEMDiags debug) {}'.format(s))
+
+    def _config_dims(self):
+        '''Input validation and layout bookkeeping (tem_diagnostics.py:266-405).'''
+        self.ncolname = self.dim_names['horz']
+        self.plevname = self.dim_names['vert']
+        self.timename = self.dim_names.get('time', DEFAULT_DIMS['time'])
+        self.data_dims = (self.ncolname, self.plevname, self.timename)
+
+        if self.q is not None:
+            raise NotImplementedError('tracer inputs (q=) are not implemented in this build yet '
+                                      '(SURVEY.md §8f rank 1); pass q=None')
+        self.ntrac = 0
+        self._q_out_file = []
+
+        lat = self.lat_native
+        lat_np = ar.raw(lat)
+        lat_np = np.asarray(lat_np.cpu() if isinstance(lat_np, torch.Tensor) else lat_np, dtype=np.float64).ravel()
+        self._lat_native_np = lat_np
+        ncol = lat_np.shape[0]
+
+        allvars = {'ua': self.ua, 'va': self.va, 'ta': self.ta, 'wap': self.wap}
+        self._kind = ar.kind_of(self.ua)
+        self._in_dims = {}
+        for var, dat in allvars.items():
+            if ar.kind_of(dat) != self._kind:
+                raise RuntimeError('Input data for arg \'{}\' must be of the same kind as ua ({})'.format(var, self._kind))
+            r = ar.raw(dat)
+            if self._kind == 'dataarray':
+                dims = tuple(dat.dims)
+            else:
+                dims = self._dims_in
+                if dims is None:
+                    dims = self.data_dims[:r.ndim]
+                dims = tuple({'horz': self.ncolname, 'vert': self.plevname, 'time': self.timename,
+                              'lev': self.plevname}.get(d, d) for d in dims)
+                if len(dims) != r.ndim:
+                    raise RuntimeError('dims={} does not match the {} dimensions of {}'.format(dims, r.ndim, var))
+            if self.ncolname not in dims:
+                raise RuntimeError('Input data {} does not contain dim {}'.format(var, self.ncolname))
+            if r.shape[dims.index(self.ncolname)] != ncol:
+                raise RuntimeError('Dimension {} in variable {} is length {}, but input parameter lat is length {}; '
+                                   'these must match!'.format(self.ncolname, var, r.shape[dims.index(self.ncolname)], ncol))
+            if len(dims) < 2 or len(dims) > 3:
+                raise RuntimeError('Input data has {0} dims, expected either 2 ({1}, {2}) or 3 ({1}, {2}, {3})'.format(
+                    len(dims), self.ncolname, self.plevname, self.timename))
+            if self.plevname not in dims:
+                raise RuntimeError('Input data {} does not contain dim {}'.format(var, self.plevname))
+            for d in dims:
+                if d not in self.data_dims:
+                    raise RuntimeError('Input data {} has unexpected dim {}'.format(var, d))
+            self._in_dims[var] = dims
+        shp = {v: {d: ar.raw(allvars[v]).shape[i] for i, d in enumerate(self._in_dims[v])} for v in allvars}
+        for v in allvars:
+            if shp[v] != shp['ua'] and {d: n for d, n in shp[v].items()} != {d: n for d, n in shp['ua'].items()}:
+                raise RuntimeError('Input variables ua and {} have different shapes'.format(v))
+        self.NCOL = ncol
+        self.NLEV = shp['ua'][self.plevname]
+        self.NT = shp['ua'].get(self.timename, 1)
+        self._log('DATA DIMENSIONS: {} x {} x {} = {} x {} x {}'.format(self.ncolname, self.plevname, self.timename,
+                                                                         self.NCOL, self.NLEV, self.NT))
+
+        # ---- vertical coordinate (hPa) and time coordinate
+        plev = None
+        if self._p_in is not None:
+            pr = ar.raw(self._p_in)
+            pr = np.asarray(pr.cpu() if isinstance(pr, torch.Tensor) else pr, dtype=np.float64)
+            units = self._p_units
+            if pr.ndim == 1:
+                if pr.shape[0] != self.NLEV:
+                    raise RuntimeError('p has length {} but the vertical dimension has length {}'.format(pr.shape[0], self.NLEV))
+                plev = pr / 100.0 if units == 'Pa' else pr
+            else:
+                pdims = tuple(self._p_in.dims) if ar.is_dataarray(self._p_in) else self._in_dims['ua']
+                if pr.ndim != len(pdims):
+                    raise RuntimeError('gridpoint pressure p must have the same dims as ua')
+                ax = pdims.index(self.plevname)
+                prm = np.moveaxis(pr, ax, 0).reshape(pr.shape[ax], -1)
+                if not np.allclose(prm, prm[:, :1], rtol=1e-12, atol=0):
+                    raise RuntimeError('gridpoint pressure p varies on a level: TEMDiagnostics needs data on a '
+                                       'pressure vertical coordinate (tem_diagnostics.py:37-40)')
+                plev = prm[:, 0] if units == 'hPa' else prm[:, 0] / 100.0
+        elif self._kind == 'dataarray':
+            plev = ar.coord_values(self.ua, self.plevname)
+            if plev is not None:
+                plev = np.asarray(plev, dtype=np.float64)
+        if plev is None:
+            raise RuntimeError('pressure levels are required: pass p= (1-D, hPa) or DataArrays with a {} '
+                               'coordinate'.format(self.plevname))
+        time = None
+        if self._time_in is not None:
+            time = np.asarray(self._time_in)
+        elif self._kind == 'dataarray' and self.timename in self._in_dims['ua']:
+            time = ar.coord_values(self.ua, self.timename)
+        if time is None:
+            time = np.arange(self.NT)
+        self.time = time
+
+        # ---- pressure must increase to the right (tem_diagnostics.py:372-382)
+        self._flip_lev = bool(plev[0] > plev[-1])
+        self._plev_input_order = plev
+        if self._flip_lev:
+            plev = plev[::-1].copy()
+            self._log('Reversed direction of vertical dimension for all data')
+        self.plev = plev
+        self.p = self.plev * 100                                   # :385
+
+        # ---- zonal-mean latitudes (:388-396)
+        tol = 1e-6
+        assert float(180 / self.zm_dlat).is_integer(), '180 must be divisible by dlat_out'
+        self._lat_zm = np.arange(-90, 90 + self.zm_dlat, self.zm_dlat)
+        if self._lat_zm[-1] > 90 + tol:
+            self._lat_zm = self._lat_zm[:-1]
+        if not self.zm_pole_points:
+            self._lat_zm = (self._lat_zm[1:] + self._lat_zm[:-1]) / 2
+        self.ZM_N = len(self._lat_zm)
+        # ---- latitude-based quantities (:401-405)
+        self._f_zm = 2 * const.Om * np.sin(self._lat_zm * np.pi / 180)
+        self._coslat_zm = np.cos(self._lat_zm * np.pi / 180)
+        self.lat, self.coslat = self._lat_zm, self._coslat_zm
+        self.f = self._f_zm[:, np.newaxis, np.newaxis]
+
+    # ------------------------------------------------------------------
+    def _slab(self, var, t0, t1, device):
+        '''Time steps [t0, t1) of one input as a float64 device tensor [(t1-t0)*K][N] (lev in input order).'''
+        dat = {'ua': self.ua, 'va': self.va, 'ta': self.ta, 'wap': self.wap}[var]
+        r = ar.raw(dat)
+        dims = self._in_dims[var]
+        if self.timename in dims:
+            sl = [slice(None)] * r.ndim
+            sl[dims.index(self.timename)] = slice(t0, t1)
+            r = r[tuple(sl)]
+        else:
+            r = r[..., None] if isinstance(r, np.ndarray) else r.unsqueeze(-1)
+            dims = dims + (self.timename,)
+        perm = [dims.index(self.timename), dims.index(self.plevname), dims.index(self.ncolname)]
+        if isinstance(r, np.ndarray):
+            if perm != [0, 1, 2] or not r.flags.c_contiguous:
+                # upload in the input's own layout, permute on the device
+                x = ar.to_device_f64(np.ascontiguousarray(r), device).permute(*perm)
+            else:
+                x = ar.to_device_f64(r, device)
+        else:
+            x = ar.to_device_f64(r, device).permute(*perm)
+        N = self.NCOL
+        x = x.reshape(-1, N) if x.is_contiguous() else x.contiguous().reshape(-1, N)
+        if N % 2 or x.data_ptr() % 16:
+            buf = torch.zeros((x.shape[0], N + (N & 1)), dtype=torch.float64, device=device)
+            buf[:, :N] = x
+            x = buf[:, :N]
+        return x
+
+    def _compute_all(self):
+        '''_compute_potential_temperature, _decompose_zm_eddy, _compute_fluxes, _compute_derivatives
+        (tem_diagnostics.py:491-611) and every diagnostics method (:615-797), on the GPU.'''
+        eng = self.ZM._engine
+        dev = eng.device
+        K, T, N = self.NLEV, self.NT, self.NCOL
+        # theta = T (p0/p)^k per level (tem_diagnostics.py:498), in the input's level order
+        p_in = self._plev_input_order * 100
+        lev_scale = eng._dev((self.p0 / p_in) ** const.k)
+        # time-slab size: 4 fields resident at once within the byte budget
+        budget = self._slab_bytes if self._slab_bytes is not None else 16 << 30
+        ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
+        coef = torch.empty((7, T * K, eng.lpad), dtype=torch.float64, device=dev)
+        for t0 in range(0, T, ts):
+            t1 = min(T, t0 + ts)
+            xs = [self._slab(v, t0, t1, dev) for v in ('ua', 'va', 'ta', 'wap')]
+            c4 = eng.project(xs, lev_scale=lev_scale, scale_field=2, nlev=K)
+            cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
+            coef[:4, t0 * K:t1 * K] = c4
+            coef[4:, t0 * K:t1 * K] = cf
+            del xs
+        eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
+        if self._flip_lev:
+            coef = coef.reshape(7, T, K, eng.lpad).flip(2).reshape(7, T * K, eng.lpad).contiguous()
+        self._coef = coef
+        zm = eng.synth_out(coef).reshape(7, T, K, eng.M)
+        res = eng.tem_epilogue(zm, self.p, self._f_zm, self._coslat_zm, p0=self.p0)
+        self._dev_results = {n: zm[i] for i, n in enumerate(_ZM_NAMES)}
+        self._dev_results.update(res)
+        self._cache = {}
+
+    # ------------------------------------------------------------------
+    def _result(self, name, like=None, cast_like=None):
+        '''(lat, plev, time) array of one result, in the container kind of the inputs.'''
+        if name in self._cache:
+            return self._cache[name]
+        t = self._dev_results[name].permute(2, 1, 0).contiguous()      # [T][K][M] -> (M, K, T)
+        src = self.ua if cast_like is None else cast_like
+        dtype = ar.dtype_of(src)
+        r = ar.raw(src)
+        in_dev = r.device if isinstance(r, torch.Tensor) else None
+        out = ar.from_device(t, 'numpy' if self._kind == 'dataarray' else self._kind, dtype, in_dev)
+        if self._kind == 'dataarray':
+            coords = {'lat': self._lat_zm, self.plevname: self.plev, self.timename: self.time}
+            out = ar.make_dataarray(self.ua, out, ('lat', self.plevname, self.timename), coords=coords, name=name)
+        self._cache[name] = out
+        return out
+
+    # zonal means and derived intermediates (tem_diagnostics.py:412-457)
+    ub = property(lambda self: self._result('ub'))
+    vb = property(lambda self: self._result('vb', cast_like=self.va))
+    thetab = property(lambda self: self._result('thetab', cast_like=self.ta))
+    wapb = property(lambda self: self._result('wapb', cast_like=self.wap))
+    upvpb = property(lambda self: self._result('upvpb'))
+    upwappb = property(lambda self: self._result('upwappb'))
+    vptpb = property(lambda self: self._result('vptpb'))
+    dub_dp = property(lambda self: self._result('dub_dp'))
+    dthetab_dp = property(lambda self: self._result('dthetab_dp'))
+    ubcoslat = property(lambda self: self._result('ubcoslat'))
+    dubcoslat_dlat = property(lambda self: self._result('dubcoslat_dlat'))
+    psicoslat = property(lambda self: self._result('psicoslat'))
+    dpsicoslat_dlat = property(lambda self: self._result('dpsicoslat_dlat'))
+    int_vbdp = property(lambda self: self._result('int_vbdp'))
+    psi = property(lambda self: self._result('psi'))
+    dpsi_dp = property(lambda self: self._result('dpsi_dp'))
+
+    @property
+    def out_file(self):
+        if self._out_file is None:
+            warnings.warn('\'out_file\' is not set until to_netcdf() is called')
+        return self._out_file
+
+    # ---- diagnostics methods (tem_diagnostics.py:615-797); each is cast to the dtype of the input the
+    #      reference casts to (:626,643,661,678,696,714,740,757,777,795)
+    def vtem(self):
+        '''TEM northward wind [m/s] (tem_diagnostics.py:615-628)'''
+        return self._result('vtem', cast_like=self.va)
+
+    def omegatem(self):
+        '''TEM upward wind [Pa/s] (tem_diagnostics.py:632-645)'''
+        return self._result('omegatem', cast_like=self.wap)
+
+    def wtem(self):
+        '''TEM upward wind [m/s] (tem_diagnostics.py:649-663)'''
+        return self._result('wtem', cast_like=self.wap)
+
+    def psitem(self):
+        '''TEM mass stream function [kg/s] (tem_diagnostics.py:667-680)'''
+        return self._result('psitem', cast_like=self.va)
+
+    def epfy(self):
+        '''northward EP flux [m3/s2] (tem_diagnostics.py:684-698)'''
+        return self._result('epfy')
+
+    def epfz(self):
+        '''upward EP flux [m3/s2] (tem_diagnostics.py:702-716)'''
+        return self._result('epfz')
+
+    def epdiv(self):
+        '''EP flux divergence [m2/s2] (tem_diagnostics.py:720-742)'''
+        return self._result('epdiv')
+
+    def utendepfd(self):
+        '''eastward-wind tendency due to EP flux divergence [m/s2] (tem_diagnostics.py:746-759)'''
+        return self._result('utendepfd')
+
+    def utendvtem(self):
+        '''eastward-wind tendency due to TEM northward advection + Coriolis [m/s2] (tem_diagnostics.py:763-779)'''
+        return self._result('utendvtem')
+
+    def utendwtem(self):
+        '''eastward-wind tendency due to TEM upward advection [m/s2] (tem_diagnostics.py:783-797)'''
+        return self._result('utendwtem')
+
+    def to_netcdf(self, *a, **k):
+        raise NotImplementedError('netCDF output is outside the hot path of this build (SURVEY.md §2 row 10)')

@@ -1,0 +1,162 @@
+"""`sph_zonal_averager` — host-side mirror of reference PyTEMDiags/sph_zonal_mean.py:35-422.
+
+Same constructor arguments, methods, attributes and error behaviour; the matrices are never read
+from / written to `maps/*.nc` (the basis is regenerated on the GPU in milliseconds), so the
+cache-related arguments are accepted and ignored.
+"""
+import numpy as np
+import torch
+
+from . import arrays as ar
+from .engine import Engine
+
+DEFAULT_LAT_ATTRS = {'long_name': 'Latitude of Grid Cell Centers', 'standard_name': 'latitude',
+                     'units': 'degrees_north', 'axis': 'Y'}   # sph_zonal_mean.py:27-28
+
+
+class sph_zonal_averager:
+    def __init__(self, lat, lat_out, L, weights=None, grid_name=None, grid_out_name=None,
+                 ncoldim='ncol', overwrite=False, save_dest=None, debug=False, logfile=None, device=None):
+        '''
+        Zonal averages of fields on unstructured grids by spherical-harmonic (m=0) least squares.
+
+        Parameters follow the reference (sph_zonal_mean.py:36-37): `lat` native latitudes [deg] (N),
+        `lat_out` output latitudes [deg] (M), `L` maximum degree.  `weights` selects the reference's
+        deprecated quadrature inverse Y0inv = Y0^T diag(4 pi w) (sph_zonal_mean.py:72,383-386), which
+        this build does not implement (raises).  `grid_name`, `grid_out_name`, `overwrite`,
+        `save_dest` only name cache files in the reference and are ignored.  `device`: CUDA device.
+        '''
+        self.L = L
+        self.lat = lat.values if ar.is_dataarray(lat) else lat
+        self.lat_out = lat_out.values if ar.is_dataarray(lat_out) else lat_out
+        self.lat = np.asarray(self.lat.cpu() if isinstance(self.lat, torch.Tensor) else self.lat, dtype=np.float64)
+        self.lat_out = np.asarray(self.lat_out.cpu() if isinstance(self.lat_out, torch.Tensor) else self.lat_out,
+                                  dtype=np.float64)
+        self.weights = weights
+        self.grid_name = grid_name
+        self.grid_out_name = grid_out_name
+        self.save_dest = save_dest
+        self.ncoldim = ncoldim
+        self.debug = debug
+        self.logfile = logfile
+        if weights is not None:
+            raise NotImplementedError('the deprecated weights= path of the reference (Y0inv = Y0^T diag(w)) is not '
+                                      'implemented; pass weights=None for the least-squares inverse')
+        self.N = len(self.lat)
+        self.M = len(self.lat_out)
+        self.l = np.arange(self.L + 1)
+        # file names the reference would use (sph_zonal_mean.py:165-174); never touched here
+        gname = self.grid_name if self.grid_name is not None else 'ncol{}'.format(self.N)
+        goname = self.grid_out_name
+        if goname is None:
+            goname = '{}deg'.format(np.diff(self.lat_out)[0]) if self.M > 1 else 'point'
+        self.grid_name, self.grid_out_name = gname, goname
+        self.Y0_file_out = None
+        self.Y0p_file_out = None
+        self._engine = Engine(self.lat, self.lat_out, self.L, device=device)
+        self._mats = None
+
+    # ------------------------------------------------------------------
+    def sph_compute_matrices(self, overwrite=False, read_only=False, no_write=False):
+        '''Builds the basis on the GPU (sph_zonal_mean.py:302-422).  `read_only=True` means "load
+        from the cache only" in the reference; there is no cache, so it returns without computing.'''
+        if read_only:
+            return
+        self._engine.build_basis(sanity=bool(self.debug))
+        self._mats = None
+        if self.debug:
+            print('(sph_zonal_mean debug) Sanity check: sum(diag(Q^T Q)) = {} (should be {}); '
+                  'sum(offdiag) = {} (should be zero)'.format(self._engine.sanity[0], self.L + 1,
+                                                              self._engine.sanity[1]))
+
+    def _export(self):
+        if not self._engine.built:
+            return None
+        if self._mats is None:
+            self._mats = tuple(t.cpu().numpy() for t in self._engine.export_matrices())
+        return self._mats
+
+    @property
+    def Y0(self):
+        m = self._export()
+        return None if m is None else m[0]
+
+    @property
+    def Y0inv(self):
+        m = self._export()
+        return None if m is None else m[1]
+
+    @property
+    def Y0p(self):
+        m = self._export()
+        return None if m is None else m[2]
+
+    # ------------------------------------------------------------------
+    def _sph_zonal_mean_generic(self, A, native, ncol_last=False):
+        eng = self._engine
+        if not eng.built:
+            raise RuntimeError('Matrices Y0, Y0inv, and/or Y0p are undefined; either verify grid_name,'
+                               'grid_name_out, and save_dest, or call sph_compute_matrices()'
+                               'before sph_zonal_mean() or sph_zonal_mean_native()!')
+        kind = ar.kind_of(A)
+        name = getattr(A, 'name', None) if kind == 'dataarray' else None
+        if name is None:
+            name = '{unnamed variable}'
+        r = ar.raw(A)
+        dtype = ar.dtype_of(A)
+        shape = tuple(r.shape)
+        if kind == 'dataarray':
+            dims = tuple(A.dims)
+            if dims[0] != self.ncoldim or shape[0] != self.N:
+                raise RuntimeError('(sph_zonal_mean_generic() Expected the first (leftmost) '
+                                   'dimension of variable {} to be {} of length {}'.format(name, self.ncoldim, self.N))
+        elif (shape[-1] if ncol_last else shape[0]) != self.N:
+            raise RuntimeError('(sph_zonal_mean_generic() Expected the {} dimension of variable {} to be of '
+                               'length {}'.format('last' if ncol_last else 'first (leftmost)', name, self.N))
+        in_dev = r.device if isinstance(r, torch.Tensor) else None
+        x = ar.to_device_f64(r, eng.device)
+        if ncol_last and kind != 'dataarray':
+            x2 = x.reshape(-1, self.N)
+            rest = shape[:-1]
+        else:
+            x2 = x.reshape(self.N, -1).t()       # (DD, N) view of the reference's (N, DD)
+            rest = shape[1:]
+        if not (x2.is_contiguous() and self.N % 2 == 0 and x2.data_ptr() % 16 == 0):
+            ld = self.N + (self.N & 1)
+            buf = torch.zeros((x2.shape[0], ld), dtype=torch.float64, device=eng.device)
+            buf[:, :self.N] = x2
+            x2 = buf[:, :self.N]
+        coef = eng.project([x2])
+        eng.check_finite(coef, name)
+        if native:
+            res = eng.synth_native(coef[0])                # (DD, N)
+        else:
+            res = eng.synth_out(coef)[0]                   # (DD, M)
+        NN = res.shape[1]
+        if ncol_last and kind != 'dataarray':
+            res = res.reshape(tuple(rest) + (NN,))
+        else:
+            res = res.t().reshape((NN,) + tuple(rest))
+        out = ar.from_device(res.contiguous(), 'numpy' if kind == 'dataarray' else kind, dtype, in_dev)
+        if kind != 'dataarray':
+            return out
+        attrs = dict(getattr(A, 'attrs', {}) or {})
+        if native:
+            coords = {d: ar.coord_values(A, d) for d in dims if ar.coord_values(A, d) is not None}
+            odims = dims
+        else:
+            # sph_zonal_mean.py:267-273: ncol -> lat, coordinate lat_out, latitude attrs
+            odims = ('lat',) + dims[1:]
+            coords = {d: ar.coord_values(A, d) for d in dims[1:] if ar.coord_values(A, d) is not None}
+            coords['lat'] = self.lat_out
+            attrs = dict(DEFAULT_LAT_ATTRS)
+        attrs['long_name'] = 'zonal mean of {}'.format(name)
+        return ar.make_dataarray(A, out, odims, coords=coords, name=name, attrs=attrs)
+
+    def sph_zonal_mean_native(self, A, ncol_last=False):
+        '''Zonal mean evaluated at every native column (sph_zonal_mean.py:285-290).'''
+        return self._sph_zonal_mean_generic(A, True, ncol_last)
+
+    def sph_zonal_mean(self, A, ncol_last=False):
+        '''Zonal mean on the output latitudes (sph_zonal_mean.py:291-296).'''
+        return self._sph_zonal_mean_generic(A, False, ncol_last)

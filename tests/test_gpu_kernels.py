@@ -1,0 +1,99 @@
+"""Kernel-level parity (through the C ABI) against the CPU oracle.  Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+import oracle
+from pytemdiags_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10   # normwise max|d| / max|ref| (BASELINE.md parity bar)
+
+
+def nerr(x, ref):
+    return float(np.abs(np.asarray(x) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def _engine(lat, lat_out, L):
+    from pytemdiags_b200.engine import Engine
+    return Engine(lat, lat_out, L).build_basis(sanity=True)
+
+
+@pytest.mark.parametrize('ne,L', [(4, 10), (6, 25), (8, 50), (16, 100)])
+def test_basis_and_matrices(ne, L):
+    lat, lon = syn.pg2_grid(ne)
+    lat_out = oracle.zm_latitudes(1)
+    eng = _engine(lat, lat_out, L)
+    Y0, Y0inv, Y0p = (t.cpu().numpy() for t in eng.export_matrices())
+    rY0, rY0inv, rY0p = oracle.sph_matrices(lat, lat_out, L)
+    assert nerr(Y0, rY0) < 1e-12
+    assert nerr(Y0p, rY0p) < 1e-12
+    assert nerr(Y0inv, rY0inv) < 1e-10
+    # reference's own logged sanity check (sph_zonal_mean.py:393-398)
+    assert abs(eng.sanity[0] - (L + 1)) < 1e-9 and abs(eng.sanity[1]) < 1e-9
+
+
+@pytest.mark.parametrize('ne,L,K,T', [(4, 10, 5, 3), (8, 50, 12, 4), (16, 100, 9, 2), (10, 25, 40, 7)])
+def test_zonal_mean_out_and_native(ne, L, K, T):
+    import torch
+    lat, lon = syn.pg2_grid(ne)
+    lat_out = oracle.zm_latitudes(1)
+    eng = _engine(lat, lat_out, L)
+    f = syn.synth_fields(lat, lon, syn.default_plev(K), T, seed=1, fields=('ua', 'ta'))
+    N = lat.shape[0]
+    Y0, Y0inv, Y0p = oracle.sph_matrices(lat, lat_out, L)
+    xs = [torch.as_tensor(f[n].reshape(T * K, N)).cuda() for n in ('ua', 'ta')]
+    coef = eng.project(xs)
+    zm = eng.synth_out(coef).cpu().numpy()           # [2][T*K][M]
+    for i, n in enumerate(('ua', 'ta')):
+        A = np.ascontiguousarray(f[n].reshape(T * K, N).T)          # reference layout (N, DD)
+        ref = oracle.zonal_mean(A, Y0p, Y0inv).T                    # -> [DD][M]
+        assert nerr(zm[i], ref) < TOL
+        refn = oracle.zonal_mean(A, Y0, Y0inv).T
+        nat = eng.synth_native(coef[i]).cpu().numpy()
+        assert nerr(nat, refn) < TOL
+
+
+@pytest.mark.parametrize('ne,L,K,T', [(4, 10, 5, 3), (8, 50, 12, 4), (6, 25, 33, 5), (16, 100, 8, 2)])
+def test_eddy_flux_project(ne, L, K, T):
+    import torch
+    lat, lon = syn.pg2_grid(ne)
+    lat_out = oracle.zm_latitudes(1)
+    plev = syn.default_plev(K)
+    eng = _engine(lat, lat_out, L)
+    N = lat.shape[0]
+    f = syn.synth_fields(lat, lon, plev, T, seed=2)
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0))
+    ref = oracle.tem_suite(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), plev, lat, L=L)
+    C = oracle.CONSTANTS
+    scale = (C['P0'] / (plev * 100)) ** C['k']
+    xs = [torch.as_tensor(f[n].reshape(T * K, N)).cuda() for n in ('ua', 'va', 'ta', 'wap')]
+    sc = torch.as_tensor(scale).cuda()
+    coef4 = eng.project(xs, lev_scale=sc, scale_field=2, nlev=K)
+    cflux = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], coef4, sc, K)
+    zm = eng.synth_out(torch.cat([coef4, cflux], 0)).cpu().numpy().reshape(7, T, K, -1)
+    names = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb')
+    for i, n in enumerate(names):
+        got = zm[i].transpose(2, 1, 0)   # (M, K, T)
+        assert nerr(got, ref[n]) < TOL, n
+
+
+@pytest.mark.parametrize('ne,L,K,T', [(4, 10, 5, 3), (8, 50, 12, 4)])
+def test_epilogue(ne, L, K, T):
+    import torch
+    lat, lon = syn.pg2_grid(ne)
+    lat_out = oracle.zm_latitudes(1)
+    plev = syn.default_plev(K)
+    eng = _engine(lat, lat_out, L)
+    f = syn.synth_fields(lat, lon, plev, T, seed=3)
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0))
+    ref = oracle.tem_suite(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), plev, lat, L=L)
+    names = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb')
+    M = lat_out.shape[0]
+    zm = torch.zeros((7, T, K, eng.Mld), dtype=torch.float64, device='cuda')
+    for i, n in enumerate(names):
+        zm[i, :, :, :M] = torch.as_tensor(np.ascontiguousarray(ref[n].transpose(2, 1, 0)))
+    out = eng.tem_epilogue(zm[..., :M], ref['p'], ref['f'][:, 0, 0], ref['coslat'])
+    for n, v in out.items():
+        got = v.cpu().numpy().transpose(2, 1, 0)
+        assert nerr(got, ref[n]) < 1e-12, n
