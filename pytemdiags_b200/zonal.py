@@ -121,7 +121,7 @@ class sph_zonal_averager:
         else:
             x2 = x.reshape(self.N, -1).t()       # (DD, N) view of the reference's (N, DD)
             rest = shape[1:]
-        if not (x2.is_contiguous() and self.N % 2 == 0 and x2.data_ptr() % 16 == 0):
+        if not (x2.stride(1) == 1 and x2.stride(0) >= self.N and x2.stride(0) % 2 == 0 and x2.data_ptr() % 16 == 0):
             ld = self.N + (self.N & 1)
             buf = torch.zeros((x2.shape[0], ld), dtype=torch.float64, device=eng.device)
             buf[:, :self.N] = x2

@@ -1,0 +1,146 @@
+"""Public-API parity (TEMDiagnostics / sph_zonal_averager) against the CPU oracle on a B200."""
+import numpy as np
+import pytest
+
+import oracle
+from pytemdiags_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def nerr(x, ref):
+    return float(np.abs(np.asarray(x) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def _case(ne, K, T, seed, plev=None, latlon=None):
+    if latlon:
+        lat, lon = syn.latlon_grid(*latlon)
+    else:
+        lat, lon = syn.pg2_grid(ne)
+    plev = syn.default_plev(K) if plev is None else plev
+    f = syn.synth_fields(lat, lon, plev, T, seed=seed)
+    return lat, lon, plev, f
+
+
+def _ref(f, plev, lat, L, **kw):
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0))
+    return oracle.tem_suite(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), plev, lat, L=L, **kw)
+
+
+ALL = oracle.TEM_OUTPUTS + oracle.TEM_INTERMEDIATES
+
+
+def _check(tem, ref, tol=TOL):
+    for n in ALL:
+        got = getattr(tem, n)
+        got = got() if callable(got) else got
+        assert got.shape == ref[n].shape, n
+        assert nerr(got, ref[n]) < tol, (n, nerr(got, ref[n]))
+
+
+@pytest.mark.parametrize('ne,K,T,L', [(4, 6, 2, 10), (8, 12, 3, 50), (16, 10, 2, 100)])
+def test_tem_suite_time_lev_ncol(ne, K, T, L):
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, plev, f = _case(ne, K, T, seed=1)
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=L, dims=('time', 'lev', 'ncol'), debug_level=0)
+    _check(tem, _ref(f, plev, lat, L))
+
+
+def test_tem_suite_reference_layout_and_reversed_plev():
+    """(ncol, plev, time) inputs with plev descending: outputs must come back model-top-first
+    (tem_diagnostics.py:372-382)."""
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, plev, f = _case(6, 9, 3, seed=2)
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0)[:, ::-1, :])
+    tem = TEMDiagnostics(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), lat, p=plev[::-1].copy(), L=25, debug_level=0)
+    ref = _ref(f, plev, lat, 25)
+    _check(tem, ref)
+    assert np.array_equal(tem.plev, plev)
+
+
+def test_tem_suite_slabbed_and_float32():
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, plev, f = _case(6, 7, 5, seed=3)
+    f32 = {k: v.astype(np.float32) for k, v in f.items()}
+    N = lat.shape[0]
+    tem = TEMDiagnostics(f32['ua'], f32['va'], f32['ta'], f32['wap'], plev, lat, L=25, dims=('time', 'lev', 'ncol'),
+                         debug_level=0, slab_bytes=2 * 4 * 8 * 7 * N)   # two time steps per slab
+    ref = _ref({k: v.astype(np.float64) for k, v in f32.items()}, plev, lat, 25)
+    assert tem.vtem().dtype == np.float32
+    for n in oracle.TEM_OUTPUTS:
+        assert nerr(getattr(tem, n)(), ref[n]) < 1e-6, n      # float32 output rounding
+
+
+def test_tem_suite_torch_cuda_inputs_and_pole_points():
+    import torch
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, plev, f = _case(8, 8, 2, seed=4)
+    dv = {k: torch.as_tensor(v).cuda() for k, v in f.items()}
+    tem = TEMDiagnostics(dv['ua'], dv['va'], dv['ta'], dv['wap'], plev, lat, L=30, dims=('time', 'lev', 'ncol'),
+                         debug_level=0, zm_dlat=2, zm_pole_points=False)
+    ref = _ref(f, plev, lat, 30, zm_dlat=2)
+    for n in oracle.TEM_OUTPUTS:
+        got = getattr(tem, n)()
+        assert isinstance(got, torch.Tensor) and got.is_cuda
+        assert nerr(got.cpu().numpy(), ref[n]) < TOL, n
+
+
+def test_tem_latlon_grid():
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, plev, f = _case(None, 6, 2, seed=5, latlon=(45, 90))
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=20, dims=('time', 'lev', 'ncol'), debug_level=0)
+    _check(tem, _ref(f, plev, lat, 20))
+
+
+def test_zonal_averager_known_answers():
+    """Analytic checks of reference tests_sph_zonal_mean.py:331-347,465-475 on a synthetic pg2 grid."""
+    import scipy.special as sp
+    from pytemdiags_b200 import sph_zonal_averager
+    lat, lon = syn.pg2_grid(15)
+    lat_out = np.arange(-89.5, 90.5, 1)
+    colat, colat_out = np.deg2rad(90 - lat), np.deg2rad(90 - lat_out)
+    lonr = np.deg2rad(lon)
+    ZM = sph_zonal_averager(lat, lat_out, 40)
+    assert ZM.Y0 is None
+    with pytest.raises(RuntimeError):
+        ZM.sph_zonal_mean(np.zeros(lat.shape[0]))
+    ZM.sph_compute_matrices()
+    y21 = sp.sph_harm_y(2, 1, colat, lonr).real
+    y20 = sp.sph_harm_y(2, 0, colat, lonr).real
+    f1 = np.sin(lonr)
+    f2 = np.deg2rad(lat) ** 2 + 1
+    assert np.abs(ZM.sph_zonal_mean(y21)).max() < 1e-3
+    assert np.abs(ZM.sph_zonal_mean(f1)).max() < 2e-2
+    assert np.allclose(ZM.sph_zonal_mean(y20), sp.sph_harm_y(2, 0, colat_out, 0).real, atol=1e-12)
+    assert np.allclose(ZM.sph_zonal_mean(f2), np.deg2rad(lat_out) ** 2 + 1, rtol=2e-2)
+    # zonally symmetric input is reproduced on the native grid (tests_sph_zonal_mean.py:152-204)
+    assert np.allclose(ZM.sph_zonal_mean_native(y20), y20, atol=1e-12)
+    # multi-dimensional input, reference layout (ncol, lev, time), and the oracle
+    A = np.random.default_rng(0).standard_normal((lat.shape[0], 3, 4))
+    Y0, Y0inv, Y0p = oracle.sph_matrices(lat, lat_out, 40)
+    assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < TOL
+    assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < TOL
+    assert nerr(ZM.Y0inv, Y0inv) < TOL and nerr(ZM.Y0, Y0) < 1e-12 and nerr(ZM.Y0p, Y0p) < 1e-12
+
+
+def test_error_behaviour():
+    from pytemdiags_b200 import TEMDiagnostics, sph_zonal_averager
+    lat, lon, plev, f = _case(4, 5, 2, seed=6)
+    bad = f['ua'].copy()
+    bad[1, 2, 3] = np.nan
+    with pytest.raises(RuntimeError, match='nans'):
+        TEMDiagnostics(bad, f['va'], f['ta'], f['wap'], plev, lat, L=10, dims=('time', 'lev', 'ncol'), debug_level=0)
+    with pytest.raises(RuntimeError, match='must match'):
+        TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat[:-2], L=10, dims=('time', 'lev', 'ncol'), debug_level=0)
+    with pytest.raises(AssertionError):
+        TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=10, dims=('time', 'lev', 'ncol'), debug_level=0, zm_dlat=7)
+    with pytest.raises(RuntimeError, match='rank-deficient'):
+        sph_zonal_averager(lat, np.arange(-89.5, 90, 1.0), 300).sph_compute_matrices()
+    ZM = sph_zonal_averager(lat, np.arange(-89.5, 90, 1.0), 8)
+    ZM.sph_compute_matrices()
+    with pytest.raises(RuntimeError, match='length'):
+        ZM.sph_zonal_mean(np.zeros(lat.shape[0] + 1))
+    x = np.zeros(lat.shape[0]); x[5] = np.nan
+    with pytest.raises(RuntimeError, match='nans'):
+        ZM.sph_zonal_mean(x)
