@@ -15,6 +15,8 @@
 // B operand of both: "MN-major" (contraction over tile rows) in GEMM1, "K-major" in GEMM2.
 // C_f lives in shared memory for the CTA's lifetime (row-major, row stride = 4 or 12 mod 16
 // doubles so that the GEMM1 A fragments are bank-conflict-free under the mnmajor_k permutation).
+#include <cstdlib>
+
 #include "temd_common.cuh"
 #include "temd_internal.h"
 
@@ -37,6 +39,7 @@ struct EddyParams {
     int stages;
     int nlev;
     int qbox;          // rows per QT TMA box (divides lpad, <= 256)
+    unsigned skew_ns;  // initial delay of warps 4..7
     const double* coef4;      // [4][rows][lpad]
     const double* lev_scale;  // [nlev] or null
     double* part;             // [nsplit][3][rows][lpad]
@@ -118,16 +121,17 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
             Cs[(size_t)(f * BM + r) * p.ls + l] = (row < p.rows) ? p.coef4[((size_t)f * p.rows + row) * lpad + l] : 0.0;
         }
     }
-    named_bar_sync(1, ED_WARPS * 32);
+    named_bar_sync(7, ED_WARPS * 32);
 
-    // GEMM1 roles
-    int mi1, f1, jn1;
-    if (MT == 4) { mi1 = warp & 3; f1 = (warp >> 2) * 2; jn1 = 0; }
-    else if (MT == 2) { mi1 = warp & 1; f1 = warp >> 1; jn1 = 0; }
-    else { mi1 = 0; f1 = warp >> 1; jn1 = warp & 1; }
-    // GEMM2 roles
-    const int mi2 = warp % MT;
-    const int wq = warp / MT;
+    // Warp roles.  The warps that produce the eddies of m-tile `mi` (GEMM1) are exactly the warps that
+    // consume them (GEMM2), so the E hand-off needs only a barrier among that group (64/128/256
+    // threads), not the whole CTA; the groups are laid out so that the two warps sharing an SM
+    // sub-partition (warp % 4) belong to different groups and carry complementary GEMM2 loads.
+    int mi1, f1, jn1, mi2, wq;
+    if (MT == 4) { mi1 = warp >> 1; f1 = (warp & 1) * 2; jn1 = 0; mi2 = mi1; wq = (warp & 1) ^ ((warp >> 2) & 1); }
+    else if (MT == 2) { mi1 = warp >> 2; f1 = warp & 3; jn1 = 0; mi2 = mi1; wq = (warp & 3) ^ (mi1 ? 3 : 0); }
+    else { mi1 = 0; f1 = warp >> 1; jn1 = warp & 1; mi2 = 0; wq = warp; }
+    const int grp_bar = 1 + mi1, grp_threads = NW2 * 32;
     const int j_begin = (wq * p.nt) / NW2;
     const int j_end = ((wq + 1) * p.nt) / NW2;
 
@@ -154,6 +158,10 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     for (int kk = 0; kk < 4; kk++) coff2[kk] = kmajor_col_off(g, t, kk);
     const uint32_t e_row_off = (uint32_t)((mi2 * 8 + g) * TILE_ROW_BYTES);
     const uint32_t q_off = 4 * XF_BYTES;
+
+    // de-phase the two warps of every SM sub-partition by about half a chunk so that one warp's
+    // GEMM1 -> eddy -> barrier -> GEMM2 transition overlaps the other's steady DMMA stream
+    if (p.skew_ns > 0 && warp >= 4) __nanosleep(p.skew_ns);
 
     for (int i = 0; i < nloc; i++) {
         const int s = i % STAGES;
@@ -201,7 +209,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
                 sts128(addr, sc * x.x - sacc[ff][nn][0], sc * x.y - sacc[ff][nn][1]);
             }
         }
-        named_bar_sync(1, ED_WARPS * 32);
+        named_bar_sync(grp_bar, grp_threads);
 
         // ---------------- GEMM2: acc += (E_a .* E_b) * QT^T (contraction over the 16 columns) ----------------
 #pragma unroll
@@ -290,6 +298,7 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     if ((rc = make_tma_2d(&maps.q, qt, (uint64_t)ncol, (uint64_t)lpad, ld_q * sizeof(double), TILE_K, qd * 8))) return rc;
     EddyParams p;
     p.qbox = qd * 8;
+    { const char* e = getenv("TEMD_EDDY_SKEW_NS"); p.skew_ns = e ? (unsigned)atoi(e) : 1500u; }
     p.rows = rows;
     p.nchunks = (ncol + TILE_K - 1) / TILE_K;
     p.nsplit = nsplit;

@@ -248,7 +248,8 @@ class TEMDiagnostics:
 
     # ------------------------------------------------------------------
     def _slab(self, var, t0, t1, device):
-        '''Time steps [t0, t1) of one input as a float64 device tensor [(t1-t0)*K][N] (lev in input order).'''
+        '''Time steps [t0, t1) of one input as a float64 device tensor [(t1-t0)*K][N] (lev in input order).
+        Host arrays are copied with non_blocking=True (a true async DMA when the array is pinned).'''
         dat = {'ua': self.ua, 'va': self.va, 'ta': self.ta, 'wap': self.wap}[var]
         r = ar.raw(dat)
         dims = self._in_dims[var]
@@ -260,14 +261,11 @@ class TEMDiagnostics:
             r = r[..., None] if isinstance(r, np.ndarray) else r.unsqueeze(-1)
             dims = dims + (self.timename,)
         perm = [dims.index(self.timename), dims.index(self.plevname), dims.index(self.ncolname)]
-        if isinstance(r, np.ndarray):
-            if perm != [0, 1, 2] or not r.flags.c_contiguous:
-                # upload in the input's own layout, permute on the device
-                x = ar.to_device_f64(np.ascontiguousarray(r), device).permute(*perm)
-            else:
-                x = ar.to_device_f64(r, device)
-        else:
-            x = ar.to_device_f64(r, device).permute(*perm)
+        if isinstance(r, np.ndarray) and not r.flags.c_contiguous and not r.flags.f_contiguous:
+            r = np.ascontiguousarray(r)     # strided host slice (time is not the leading dim): pack on the host
+        x = ar.to_device_f64(r, device, non_blocking=True)
+        if perm != [0, 1, 2]:
+            x = x.permute(*perm)            # layout change happens on the device
         N = self.NCOL
         x = x.reshape(-1, N) if x.is_contiguous() else x.contiguous().reshape(-1, N)
         if N % 2 or x.data_ptr() % 16:
@@ -278,25 +276,47 @@ class TEMDiagnostics:
 
     def _compute_all(self):
         '''_compute_potential_temperature, _decompose_zm_eddy, _compute_fluxes, _compute_derivatives
-        (tem_diagnostics.py:491-611) and every diagnostics method (:615-797), on the GPU.'''
+        (tem_diagnostics.py:491-611) and every diagnostics method (:615-797), on the GPU.
+
+        The record is processed in time slabs (time steps are independent): while slab i is in the
+        project / eddy-flux kernels on the compute stream, slab i+1 is copied host->device (or
+        re-laid-out) on a second stream.'''
         eng = self.ZM._engine
         dev = eng.device
         K, T, N = self.NLEV, self.NT, self.NCOL
         # theta = T (p0/p)^k per level (tem_diagnostics.py:498), in the input's level order
         p_in = self._plev_input_order * 100
         lev_scale = eng._dev((self.p0 / p_in) ** const.k)
-        # time-slab size: 4 fields resident at once within the byte budget
-        budget = self._slab_bytes if self._slab_bytes is not None else 16 << 30
+        on_host = not isinstance(ar.raw(self.ua), torch.Tensor) or not ar.raw(self.ua).is_cuda
+        budget = self._slab_bytes if self._slab_bytes is not None else ((2 << 30) if on_host else (16 << 30))
         ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
         coef = torch.empty((7, T * K, eng.lpad), dtype=torch.float64, device=dev)
-        for t0 in range(0, T, ts):
-            t1 = min(T, t0 + ts)
-            xs = [self._slab(v, t0, t1, dev) for v in ('ua', 'va', 'ta', 'wap')]
-            c4 = eng.project(xs, lev_scale=lev_scale, scale_field=2, nlev=K)
-            cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
-            coef[:4, t0 * K:t1 * K] = c4
-            coef[4:, t0 * K:t1 * K] = cf
-            del xs
+        names = ('ua', 'va', 'ta', 'wap')
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+
+            def fetch(t0):
+                t1 = min(T, t0 + ts)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    xs = [self._slab(v, t0, t1, dev) for v in names]
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                return xs, ev, t0, t1
+
+            nxt = fetch(0)
+            while nxt is not None:
+                xs, ev, t0, t1 = nxt
+                nxt = fetch(t1) if t1 < T else None
+                main.wait_event(ev)
+                for x in xs:
+                    x.record_stream(main)
+                c4 = eng.project(xs, lev_scale=lev_scale, scale_field=2, nlev=K)
+                cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
+                coef[:4, t0 * K:t1 * K] = c4
+                coef[4:, t0 * K:t1 * K] = cf
+                del xs
         eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
         if self._flip_lev:
             coef = coef.reshape(7, T, K, eng.lpad).flip(2).reshape(7, T * K, eng.lpad).contiguous()

@@ -10,6 +10,27 @@ import torch
 from . import arrays as ar
 from .engine import Engine
 
+# Engines (plan + orthonormalised basis in HBM) are kept per (grid, output grid, L, device), the device-memory
+# analogue of the reference's on-disk `maps/Y0_*.nc` cache (sph_zonal_mean.py:165-177,330-345).
+_ENGINE_CACHE = {}
+_ENGINE_CACHE_MAX = 2
+
+
+def _cached_engine(lat, lat_out, L, device, overwrite=False):
+    import hashlib
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (hashlib.sha1(lat.tobytes()).hexdigest(), hashlib.sha1(lat_out.tobytes()).hexdigest(), int(L), str(dev))
+    if overwrite:
+        _ENGINE_CACHE.pop(key, None)
+    eng = _ENGINE_CACHE.get(key)
+    if eng is None:
+        while len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
+            _ENGINE_CACHE.pop(next(iter(_ENGINE_CACHE)))
+        eng = Engine(lat, lat_out, L, device=dev)
+        _ENGINE_CACHE[key] = eng
+    return eng
+
+
 DEFAULT_LAT_ATTRS = {'long_name': 'Latitude of Grid Cell Centers', 'standard_name': 'latitude',
                      'units': 'degrees_north', 'axis': 'Y'}   # sph_zonal_mean.py:27-28
 
@@ -53,7 +74,9 @@ class sph_zonal_averager:
         self.grid_name, self.grid_out_name = gname, goname
         self.Y0_file_out = None
         self.Y0p_file_out = None
-        self._engine = Engine(self.lat, self.lat_out, self.L, device=device)
+        if not torch.cuda.is_available():
+            raise RuntimeError('pytemdiags_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self._engine = _cached_engine(self.lat, self.lat_out, self.L, device, overwrite=overwrite)
         self._mats = None
 
     # ------------------------------------------------------------------
@@ -62,6 +85,8 @@ class sph_zonal_averager:
         from the cache only" in the reference; there is no cache, so it returns without computing.'''
         if read_only:
             return
+        if self._engine.built and not overwrite:
+            return                                   # "read from the cache" (sph_zonal_mean.py:330-345)
         self._engine.build_basis(sanity=bool(self.debug))
         self._mats = None
         if self.debug:

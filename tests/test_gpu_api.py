@@ -101,7 +101,7 @@ def test_zonal_averager_known_answers():
     lat_out = np.arange(-89.5, 90.5, 1)
     colat, colat_out = np.deg2rad(90 - lat), np.deg2rad(90 - lat_out)
     lonr = np.deg2rad(lon)
-    ZM = sph_zonal_averager(lat, lat_out, 40)
+    ZM = sph_zonal_averager(lat, lat_out, 40, overwrite=True)
     assert ZM.Y0 is None
     with pytest.raises(RuntimeError):
         ZM.sph_zonal_mean(np.zeros(lat.shape[0]))
