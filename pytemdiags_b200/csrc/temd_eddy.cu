@@ -22,8 +22,6 @@
 
 namespace temd {
 
-constexpr int ED_WARPS = 8;
-constexpr int ED_THREADS = (ED_WARPS + 1) * 32;
 constexpr int ED_SMEM_LIMIT = 232448 - 2048;   // 227 KB minus alignment slack and static barriers
 constexpr int ED_MAX_STAGES = 4;
 
@@ -39,7 +37,6 @@ struct EddyParams {
     int stages;
     int nlev;
     int qbox;          // rows per QT TMA box (divides lpad, <= 256)
-    unsigned skew_ns;  // initial delay of warps 4..7
     const double* coef4;      // [4][rows][lpad]
     const double* lev_scale;  // [nlev] or null
     double* part;             // [nsplit][3][rows][lpad]
@@ -51,14 +48,41 @@ __host__ __device__ inline int eddy_ls(int lpad) {
     return ls;
 }
 
-template <int BM, int NJ>
-__global__ void __launch_bounds__(ED_THREADS, 1)
+// GEMM2 inner step for one 16-column chunk: CNT (<= NJ) n8-tiles of this warp, 3 flux products.
+template <int CNT, int NJ, int XF_BYTES>
+__device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st, uint32_t qs, uint32_t e_row_off,
+                                           const uint32_t (&coff2)[4], int g, int j_begin) {
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        const uint32_t eo = st + e_row_off + coff2[kk];
+        const double eu = lds64(eo);
+        const double ev = lds64(eo + XF_BYTES);
+        const double et = lds64(eo + 2 * XF_BYTES);
+        const double ew = lds64(eo + 3 * XF_BYTES);
+        const double a_uv = eu * ev, a_uw = eu * ew, a_vt = ev * et;
+        const uint32_t bo = qs + (uint32_t)((j_begin * 8 + g) * TILE_ROW_BYTES) + coff2[kk];
+        double b[CNT];
+#pragma unroll
+        for (int jj = 0; jj < CNT; jj++) b[jj] = lds64(bo + (uint32_t)jj * 8u * TILE_ROW_BYTES);
+#pragma unroll
+        for (int jj = 0; jj < CNT; jj++) {
+            dmma(acc[0][jj][0], acc[0][jj][1], a_uv, b[jj]);
+            dmma(acc[1][jj][0], acc[1][jj][1], a_uw, b[jj]);
+            dmma(acc[2][jj][0], acc[2][jj][1], a_vt, b[jj]);
+        }
+    }
+}
+
+template <int BM, int NJ, int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 1)
 k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     constexpr int MT = BM / 8;          // m8-tiles per CTA
-    constexpr int NW2 = ED_WARPS / MT;  // warps sharing one m-tile in GEMM2
-    constexpr int NF1 = (MT == 4) ? 2 : 1;   // GEMM1: fields per warp
-    constexpr int NN1 = (MT == 1) ? 1 : 2;   // GEMM1: n8-tiles (of the 16-column chunk) per warp
+    constexpr int NW2 = WARPS / MT;     // warps per m-tile group (2, 4, 8 or 16)
+    // GEMM1: a group owns 8 units (4 fields x 2 n8-tiles of the 16-column chunk) of its m-tile
+    constexpr int NF1 = (NW2 == 2) ? 2 : 1;   // fields per warp
+    constexpr int NN1 = (NW2 >= 8) ? 1 : 2;   // n8-tiles per warp
     constexpr int XF_BYTES = BM * TILE_ROW_BYTES;   // one field's X tile
+    static_assert(NW2 == 2 || NW2 == 4 || NW2 == 8, "unsupported warp layout");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bars[2 * ED_MAX_STAGES];
@@ -82,12 +106,12 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     const uint32_t cs_base = smem_base + STAGES * stage_bytes;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), ED_WARPS); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == ED_WARPS) {
+    if (warp == WARPS) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             for (int f = 0; f < 4; f++) tma_prefetch_desc(&maps.x[f]);
@@ -109,36 +133,34 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
 
     // ------------------------------ consumers ------------------------------
     const int g = lane >> 2, t = lane & 3;
-    const int tid = threadIdx.x;   // 0..255
+    const int tid = threadIdx.x;   // 0 .. WARPS*32-1
     // spectral coefficients of the 4 fields for this CTA's rows -> Cs[f][r][LS]
-    {
-        const int total = 4 * BM * lpad;
-        for (int e = tid; e < total; e += ED_WARPS * 32) {
-            const int l = e % lpad;
-            const int r = (e / lpad) % BM;
-            const int f = e / (lpad * BM);
-            const int row = row0 + r;
-            Cs[(size_t)(f * BM + r) * p.ls + l] = (row < p.rows) ? p.coef4[((size_t)f * p.rows + row) * lpad + l] : 0.0;
-        }
+    for (int fr = warp; fr < 4 * BM; fr += WARPS) {
+        const int f = fr / BM, r = fr % BM;
+        const int row = row0 + r;
+        const double* src = p.coef4 + ((size_t)f * p.rows + row) * lpad;
+        double* dst = Cs + (size_t)fr * p.ls;
+        for (int l = lane; l < lpad; l += 32) dst[l] = (row < p.rows) ? src[l] : 0.0;
     }
-    named_bar_sync(7, ED_WARPS * 32);
+    (void)tid;
+    named_bar_sync(15, WARPS * 32);
 
     // Warp roles.  The warps that produce the eddies of m-tile `mi` (GEMM1) are exactly the warps that
-    // consume them (GEMM2), so the E hand-off needs only a barrier among that group (64/128/256
-    // threads), not the whole CTA; the groups are laid out so that the two warps sharing an SM
-    // sub-partition (warp % 4) belong to different groups and carry complementary GEMM2 loads.
-    int mi1, f1, jn1, mi2, wq;
-    if (MT == 4) { mi1 = warp >> 1; f1 = (warp & 1) * 2; jn1 = 0; mi2 = mi1; wq = (warp & 1) ^ ((warp >> 2) & 1); }
-    else if (MT == 2) { mi1 = warp >> 2; f1 = warp & 3; jn1 = 0; mi2 = mi1; wq = (warp & 3) ^ (mi1 ? 3 : 0); }
-    else { mi1 = 0; f1 = warp >> 1; jn1 = warp & 1; mi2 = 0; wq = warp; }
-    const int grp_bar = 1 + mi1, grp_threads = NW2 * 32;
+    // consume them (GEMM2), so the E hand-off needs only a barrier among that group, not the whole
+    // CTA.  Groups are laid out so that the warps sharing an SM sub-partition (warp % 4) belong to
+    // different groups and carry complementary GEMM2 loads.
+    const int mi = warp / NW2, r_in = warp % NW2;
+    const int f1 = (NW2 == 2) ? r_in * 2 : (NW2 == 4 ? r_in : (r_in >> 1) & 3);
+    const int jn1 = (NW2 >= 8) ? (r_in & 1) : 0;
+    const int wq = (r_in + ((NW2 == 2) ? (mi >> 1) : mi)) % NW2;
+    const int grp_bar = 1 + mi, grp_threads = NW2 * 32;
     const int j_begin = (wq * p.nt) / NW2;
-    const int j_end = ((wq + 1) * p.nt) / NW2;
+    const int j_cnt = ((wq + 1) * p.nt) / NW2 - j_begin;      // NJ or NJ-1 (NJ = ceil(nt / NW2))
 
-    // theta scale for this thread's GEMM1 row (field 2 only)
+    // theta scale for this thread's row (field 2 only)
     double tscale = 1.0;
     {
-        const int row = row0 + mi1 * 8 + g;
+        const int row = row0 + mi * 8 + g;
         if (p.lev_scale != nullptr && row < p.rows) tscale = p.lev_scale[row % p.nlev];
     }
 
@@ -150,18 +172,14 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
 
     // per-thread constant offsets
     const int k1c0 = mnmajor_k(t, 0), k1c1 = mnmajor_k(t, 1);
-    uint32_t a1_off[NF1];   // GEMM1 A: Cs[(f*BM + mi1*8 + g)][.]
+    uint32_t a1_off[NF1];   // GEMM1 A: Cs[(f*BM + mi*8 + g)][.]
 #pragma unroll
-    for (int ff = 0; ff < NF1; ff++) a1_off[ff] = cs_base + (uint32_t)(((f1 + ff) * BM + mi1 * 8 + g) * p.ls) * 8u;
+    for (int ff = 0; ff < NF1; ff++) a1_off[ff] = cs_base + (uint32_t)(((f1 + ff) * BM + mi * 8 + g) * p.ls) * 8u;
     uint32_t coff2[4];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) coff2[kk] = kmajor_col_off(g, t, kk);
-    const uint32_t e_row_off = (uint32_t)((mi2 * 8 + g) * TILE_ROW_BYTES);
+    const uint32_t e_row_off = (uint32_t)((mi * 8 + g) * TILE_ROW_BYTES);
     const uint32_t q_off = 4 * XF_BYTES;
-
-    // de-phase the two warps of every SM sub-partition by about half a chunk so that one warp's
-    // GEMM1 -> eddy -> barrier -> GEMM2 transition overlaps the other's steady DMMA stream
-    if (p.skew_ns > 0 && warp >= 4) __nanosleep(p.skew_ns);
 
     for (int i = 0; i < nloc; i++) {
         const int s = i % STAGES;
@@ -202,7 +220,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
             const double sc = (f == 2) ? tscale : 1.0;
 #pragma unroll
             for (int nn = 0; nn < NN1; nn++) {
-                const int row = mi1 * 8 + g;
+                const int row = mi * 8 + g;
                 const int col = (jn1 + nn) * 8 + 2 * t;
                 const uint32_t addr = st + f * XF_BYTES + swz_off(row, col);
                 const double2 x = lds128(addr);
@@ -212,26 +230,9 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
         named_bar_sync(grp_bar, grp_threads);
 
         // ---------------- GEMM2: acc += (E_a .* E_b) * QT^T (contraction over the 16 columns) ----------------
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            const uint32_t eo = st + e_row_off + coff2[kk];
-            const double eu = lds64(eo);
-            const double ev = lds64(eo + XF_BYTES);
-            const double et = lds64(eo + 2 * XF_BYTES);
-            const double ew = lds64(eo + 3 * XF_BYTES);
-            const double a_uv = eu * ev, a_uw = eu * ew, a_vt = ev * et;
-            const uint32_t bo = qs + (uint32_t)(g * TILE_ROW_BYTES) + coff2[kk];
-#pragma unroll
-            for (int jj = 0; jj < NJ; jj++) {
-                const int j = j_begin + jj;
-                if (j < j_end) {
-                    const double b = lds64(bo + (uint32_t)j * 8u * TILE_ROW_BYTES);
-                    dmma(acc[0][jj][0], acc[0][jj][1], a_uv, b);
-                    dmma(acc[1][jj][0], acc[1][jj][1], a_uw, b);
-                    dmma(acc[2][jj][0], acc[2][jj][1], a_vt, b);
-                }
-            }
-        }
+        if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES>(acc, st, qs, e_row_off, coff2, g, j_begin);
+        else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES>(acc, st, qs, e_row_off, coff2, g, j_begin);
+
         // the E tiles were written through the generic proxy; order them before the next TMA refill
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
@@ -239,15 +240,14 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     }
 
     // ------------------------------ split-K partials ------------------------------
-    const int row = row0 + mi2 * 8 + g;
+    const int row = row0 + mi * 8 + g;
     if (row < p.rows) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             double* out = p.part + (((size_t)split * 3 + a) * p.rows + row) * lpad;
 #pragma unroll
             for (int jj = 0; jj < NJ; jj++) {
-                const int j = j_begin + jj;
-                if (j < j_end) *reinterpret_cast<double2*>(out + j * 8 + 2 * t) = make_double2(acc[a][jj][0], acc[a][jj][1]);
+                if (jj < j_cnt) *reinterpret_cast<double2*>(out + (j_begin + jj) * 8 + 2 * t) = make_double2(acc[a][jj][0], acc[a][jj][1]);
             }
         }
     }
@@ -274,12 +274,12 @@ int eddy_pick_split(int rows, int lpad, int nchunks, int sms) {
 
 size_t eddy_workspace_doubles(int rows, int lpad, int nsplit) { return (size_t)nsplit * 3 * rows * lpad; }
 
-template <int BM, int NJ>
+template <int BM, int NJ, int WARPS>
 static int launch_eddy_t(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (p.rows + BM - 1) / BM;
-    k_eddy<BM, NJ><<<ntiles * p.nsplit, ED_THREADS, smem, stream>>>(maps, p);
+    k_eddy<BM, NJ, WARPS><<<ntiles * p.nsplit, (WARPS + 1) * 32, smem, stream>>>(maps, p);
     return (int)cudaGetLastError();
 }
 
@@ -298,7 +298,6 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     if ((rc = make_tma_2d(&maps.q, qt, (uint64_t)ncol, (uint64_t)lpad, ld_q * sizeof(double), TILE_K, qd * 8))) return rc;
     EddyParams p;
     p.qbox = qd * 8;
-    { const char* e = getenv("TEMD_EDDY_SKEW_NS"); p.skew_ns = e ? (unsigned)atoi(e) : 1500u; }
     p.rows = rows;
     p.nchunks = (ncol + TILE_K - 1) / TILE_K;
     p.nsplit = nsplit;
@@ -312,15 +311,21 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     int smem;
     p.stages = eddy_stages(nt, bm, &smem);
     if (p.stages < 2) return temd_set_error(-1, "eddy_flux_project: not enough shared memory for lpad = %d", lpad);
-    const int nw2 = ED_WARPS / (bm / 8);
+    // 16 consumer warps (4 per SM sub-partition) hide the per-chunk phase changes better than 8; the
+    // BM = 8 layout has only 8 GEMM1 units per chunk, so it stays at 8 warps.
+    int warps = (bm == 8) ? 8 : 16;
+    { const char* e = getenv("TEMD_EDDY_WARPS"); if (e && bm != 8) warps = atoi(e) == 8 ? 8 : 16; }
+    const int nw2 = warps / (bm / 8);
     const int nj = (nt + nw2 - 1) / nw2;
     rc = -1;
-#define ED_CASE(BM_, NJ_) if (bm == BM_ && nj == NJ_) rc = launch_eddy_t<BM_, NJ_>(maps, p, smem, stream);
-#define ED_CASES(BM_) ED_CASE(BM_, 1) ED_CASE(BM_, 2) ED_CASE(BM_, 3) ED_CASE(BM_, 4) ED_CASE(BM_, 5) ED_CASE(BM_, 6) ED_CASE(BM_, 7)
-    ED_CASES(32) ED_CASES(16) ED_CASES(8)
-#undef ED_CASES
+#define ED_CASE(BM_, NJ_, W_) if (bm == BM_ && nj == NJ_ && warps == W_) rc = launch_eddy_t<BM_, NJ_, W_>(maps, p, smem, stream);
+#define ED_CASES7(BM_, W_) ED_CASE(BM_, 1, W_) ED_CASE(BM_, 2, W_) ED_CASE(BM_, 3, W_) ED_CASE(BM_, 4, W_) ED_CASE(BM_, 5, W_) ED_CASE(BM_, 6, W_) ED_CASE(BM_, 7, W_)
+#define ED_CASES4(BM_, W_) ED_CASE(BM_, 1, W_) ED_CASE(BM_, 2, W_) ED_CASE(BM_, 3, W_) ED_CASE(BM_, 4, W_)
+    ED_CASES7(32, 8) ED_CASES7(16, 8) ED_CASES7(8, 8) ED_CASES4(32, 16) ED_CASES4(16, 16)
+#undef ED_CASES7
+#undef ED_CASES4
 #undef ED_CASE
-    if (rc) return temd_set_error(rc, "eddy_flux_project: kernel launch failed (bm %d, nj %d)", bm, nj);
+    if (rc) return temd_set_error(rc, "eddy_flux_project: kernel launch failed (bm %d, nj %d, warps %d)", bm, nj, warps);
     return launch_reduce_partials(part, coef_flux, nsplit, 3, rows, lpad, nullptr, -1, 1, stream);
 }
 

@@ -10,14 +10,14 @@
 // STAGES-deep TMA/mbarrier ring (128-B swizzle); 8 consumer warps each own a 16-row strip and all
 // NTB n8-tiles, issuing DMMA.8x8x4 from conflict-free LDS.64 fragments.  Split-K partials go to a
 // workspace and are summed in a fixed order by `k_reduce_partials` (deterministic, no atomics).
+#include <cstdlib>
+
 #include "temd_common.cuh"
 #include "temd_internal.h"
 
 namespace temd {
 
 constexpr int PROJ_BM = 128;
-constexpr int PROJ_CONSUMER_WARPS = 8;
-constexpr int PROJ_THREADS = (PROJ_CONSUMER_WARPS + 1) * 32;
 
 struct ProjMaps {
     CUtensorMap x[TEMD_MAX_FIELDS];   // per field: dims {N, rows}, box {16, 128}
@@ -44,9 +44,10 @@ constexpr int proj_stages() {
     return s > 8 ? 8 : s;
 }
 
-template <int NTB>
-__global__ void __launch_bounds__(PROJ_THREADS, 1)
+template <int NTB, int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 1)
 k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
+    constexpr int MTW = PROJ_BM / 8 / WARPS;   // m8-tiles per consumer warp (2 with 8 warps, 1 with 16)
     constexpr int STAGES = proj_stages<NTB>();
     constexpr int STAGE_BYTES = proj_stage_bytes<NTB>();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,13 +76,13 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), PROJ_CONSUMER_WARPS);
+            mbar_init(empty_bar(s), WARPS);
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == PROJ_CONSUMER_WARPS) {
+    if (warp == WARPS) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&maps.x[field]);
@@ -102,16 +103,16 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
 
     // ------------------------------ DMMA consumers ------------------------------
     const int g = lane >> 2, t = lane & 3;
-    double acc[2][NTB][2];
+    double acc[MTW][NTB][2];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < MTW; i++)
 #pragma unroll
         for (int j = 0; j < NTB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     uint32_t coff[4];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) coff[kk] = kmajor_col_off(g, t, kk);
-    const uint32_t a_row_off = (warp * 16 + g) * TILE_ROW_BYTES;
+    const uint32_t a_row_off = (warp * 8 * MTW + g) * TILE_ROW_BYTES;
     const uint32_t b_row_off = PROJ_BM * TILE_ROW_BYTES + g * TILE_ROW_BYTES;
 
     for (int i = 0; i < nloc; i++) {
@@ -121,16 +122,15 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
         const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-            const double a0 = lds64(st + a_row_off + coff[kk]);
-            const double a1 = lds64(st + a_row_off + 8 * TILE_ROW_BYTES + coff[kk]);
-            double b[NTB];
+            double a[MTW], b[NTB];
+#pragma unroll
+            for (int i2 = 0; i2 < MTW; i2++) a[i2] = lds64(st + a_row_off + i2 * 8 * TILE_ROW_BYTES + coff[kk]);
 #pragma unroll
             for (int j = 0; j < NTB; j++) b[j] = lds64(st + b_row_off + j * 8 * TILE_ROW_BYTES + coff[kk]);
 #pragma unroll
-            for (int j = 0; j < NTB; j++) {
-                dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
-                dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
-            }
+            for (int j = 0; j < NTB; j++)
+#pragma unroll
+                for (int i2 = 0; i2 < MTW; i2++) dmma(acc[i2][j][0], acc[i2][j][1], a[i2], b[j]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));
@@ -139,8 +139,8 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
     // ------------------------------ epilogue: split-K partial ------------------------------
     double* out = p.part + ((size_t)split * p.nfields + field) * (size_t)p.rows * p.lpad;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const int row = row0 + warp * 16 + i * 8 + g;
+    for (int i = 0; i < MTW; i++) {
+        const int row = row0 + warp * 8 * MTW + i * 8 + g;
         if (row < p.rows) {
 #pragma unroll
             for (int j = 0; j < NTB; j++) {
@@ -178,14 +178,20 @@ int launch_reduce_partials(const double* part, double* out, int nsplit, int nfie
     return 0;
 }
 
-template <int NTB>
-static int launch_project_t(const ProjMaps& maps, const ProjParams& p, int lblocks, cudaStream_t stream) {
+template <int NTB, int WARPS>
+static int launch_project_w(const ProjMaps& maps, const ProjParams& p, int lblocks, cudaStream_t stream) {
     constexpr int smem = proj_stages<NTB>() * proj_stage_bytes<NTB>() + 1024;
-    cudaError_t e = cudaFuncSetAttribute(k_project<NTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_project<NTB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(p.tiles_per_field * p.nfields * p.nsplit, lblocks);
-    k_project<NTB><<<grid, PROJ_THREADS, smem, stream>>>(maps, p);
+    k_project<NTB, WARPS><<<grid, (WARPS + 1) * 32, smem, stream>>>(maps, p);
     return (int)cudaGetLastError();
+}
+
+template <int NTB>
+static int launch_project_t(const ProjMaps& maps, const ProjParams& p, int lblocks, cudaStream_t stream) {
+    static const int warps = [] { const char* e = getenv("TEMD_PROJECT_WARPS"); return (e && atoi(e) == 16) ? 16 : 8; }();   // 8 measured faster (34.3 vs 33.9 TFLOP/s)
+    return warps == 8 ? launch_project_w<NTB, 8>(maps, p, lblocks, stream) : launch_project_w<NTB, 16>(maps, p, lblocks, stream);
 }
 
 // pick the l-block size: balanced blocks of at most 13 n8-tiles
