@@ -95,6 +95,36 @@ enum {
 
 int temd_tem_epilogue(temd_plan* plan, const temd_epilogue_args* args, void* stream);
 
+/* Tracer TEM (tem_diagnostics.py:532-538,560-570,602-611 and the methods etfy/etfz/etdiv/qtendetfd/
+ * qtendvtem/qtendwtem :801-991) for ONE tracer.  zmq: [3][nt*nlev][ld] = qb, qpvpb, qpwappb (obtained with
+ * temd_project on q and temd_eddy_flux_project on (q, v, T, omega), whose first two products are then
+ * q'v' and q'omega').  psi / vtem / omegatem: planes written by temd_tem_epilogue.
+ * out: [TEMD_NTROUT + 2][nt*nlev][ld], last two planes scratch. */
+typedef struct temd_tracer_args {
+    int nt, nlev, nlat;
+    size_t ld;
+    const double* zmq;
+    const double* psi;
+    const double* vtem;
+    const double* omegatem;
+    const double* p;
+    const double* latr;
+    const double* gp;
+    const double* gl;
+    int p_uniform, lat_uniform;
+    double hp, hlat;
+    const double* coslat;
+    double p0, a, H;
+    double* out;
+} temd_tracer_args;
+
+enum {
+    TEMD_TROUT_DQB_DP = 0, TEMD_TROUT_QBCOSLAT, TEMD_TROUT_DQBCOSLAT_DLAT, TEMD_TROUT_ETFY, TEMD_TROUT_ETFZ,
+    TEMD_TROUT_ETDIV, TEMD_TROUT_QTENDETFD, TEMD_TROUT_QTENDVTEM, TEMD_TROUT_QTENDWTEM, TEMD_NTROUT
+};
+
+int temd_tracer_epilogue(temd_plan* plan, const temd_tracer_args* args, void* stream);
+
 /* NaN screen of sph_zonal_mean.py:219-221 done on the small coefficient block (NaNs in a field
  * propagate into its coefficients): returns 0 if all n values are finite, -2 otherwise (synchronises). */
 int temd_check_finite(const double* data, size_t n, void* stream);

@@ -72,23 +72,34 @@ def sph_basis(lat_deg, L):
     return Y0
 
 
-def sph_matrices(lat, lat_out, L, method='auto'):
+def sph_matrices(lat, lat_out, L, method='auto', basis='scipy'):
     """sph_zonal_mean.py:358-390 — Y0 (N,L+1), Y0inv (L+1,N), Y0p (M,L+1).
 
     method='lstsq' is the literal reference call `lstsq(Y0, identity(N))[0]` (needs an N x N
     identity); 'pinv' is the mathematically identical Moore-Penrose pseudo-inverse
-    (|lstsq - pinv|_max = 1.7e-17 at N=21,600).  'auto' = lstsq for N <= 6000.
+    (|lstsq - pinv|_max = 1.7e-17 at N=21,600, SURVEY.md §8c).  'auto' = lstsq for N <= 6000;
+    'normal' = normal equations, for the million-column sampled checks only.
     """
     lat = np.asarray(lat, dtype=np.float64)
     lat_out = np.asarray(lat_out, dtype=np.float64)
-    Y0 = sph_basis(lat, L)
-    Y0p = sph_basis(lat_out, L)
+    if basis == 'recurrence':
+        # O(N L) instead of SciPy's O(N L^2): only for the million-column sampled checks; the recurrence is
+        # pinned against SciPy and mpmath in tests/test_oracle_golden.py
+        Y0 = sph_basis_recurrence(np.cos(np.deg2rad(90 - lat)), L)
+        Y0p = sph_basis_recurrence(np.cos(np.deg2rad(90 - lat_out)), L)
+    else:
+        Y0 = sph_basis(lat, L)
+        Y0p = sph_basis(lat_out, L)
     if method == 'auto':
         method = 'lstsq' if lat.shape[0] <= 6000 else 'pinv'
     if method == 'lstsq':
         Y0inv = scipy.linalg.lstsq(Y0, np.identity(lat.shape[0]))[0]
     elif method == 'pinv':
         Y0inv = np.linalg.pinv(Y0)
+    elif method == 'normal':
+        # pinv(Y0) = (Y0^T Y0)^-1 Y0^T for full column rank; only for the million-column configs where
+        # an SVD of Y0 takes minutes (cond(Y0) <= 23 there, SURVEY.md §7.1)
+        Y0inv = scipy.linalg.solve(Y0.T @ Y0, Y0.T, assume_a='pos')
     else:
         raise ValueError(method)
     return Y0, Y0inv, Y0p

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libtemd.so')
 SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
     'temd_basis_build', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
-    'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_check_finite', 'temd_synth_fields',
+    'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_synth_fields',
 )
 
 # order of the output planes written by temd_tem_epilogue (enum TEMD_OUT_* in temd.h)
@@ -30,6 +30,18 @@ class EpilogueArgs(C.Structure):
                 ('p_uniform', C.c_int), ('lat_uniform', C.c_int), ('hp', C.c_double), ('hlat', C.c_double),
                 ('coslat', C.c_void_p), ('f', C.c_void_p),
                 ('p0', C.c_double), ('a', C.c_double), ('H', C.c_double), ('g0', C.c_double), ('pi', C.c_double),
+                ('out', C.c_void_p)]
+
+
+TRACER_OUTPUTS = ('dqb_dp', 'qbcoslat', 'dqbcoslat_dlat', 'etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem')
+
+
+class TracerArgs(C.Structure):
+    _fields_ = [('nt', C.c_int), ('nlev', C.c_int), ('nlat', C.c_int), ('ld', C.c_size_t),
+                ('zmq', C.c_void_p), ('psi', C.c_void_p), ('vtem', C.c_void_p), ('omegatem', C.c_void_p),
+                ('p', C.c_void_p), ('latr', C.c_void_p), ('gp', C.c_void_p), ('gl', C.c_void_p),
+                ('p_uniform', C.c_int), ('lat_uniform', C.c_int), ('hp', C.c_double), ('hlat', C.c_double),
+                ('coslat', C.c_void_p), ('p0', C.c_double), ('a', C.c_double), ('H', C.c_double),
                 ('out', C.c_void_p)]
 
 
@@ -58,6 +70,7 @@ def load():
     lib.temd_synth_native.argtypes = [vp, vp, i, vp, sz, vp]
     lib.temd_eddy_flux_project.argtypes = [vp, vp, vp, vp, vp, i, sz, vp, vp, i, vp, vp]
     lib.temd_tem_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), vp]
+    lib.temd_tracer_epilogue.argtypes = [vp, C.POINTER(TracerArgs), vp]
     lib.temd_check_finite.argtypes = [vp, sz, vp]
     lib.temd_synth_fields.argtypes = [vp, i, i, i, i, i, i, sz, vp, vp, vp, vp]
     for name in SYMBOLS:

@@ -369,6 +369,18 @@ extern "C" int temd_tem_epilogue(temd_plan* p, const temd_epilogue_args* args, v
     return 0;
 }
 
+namespace temd { int launch_tracer_epilogue(const temd_tracer_args& a, cudaStream_t stream); }
+
+extern "C" int temd_tracer_epilogue(temd_plan* p, const temd_tracer_args* args, void* stream) {
+    if (p == nullptr || args == nullptr) return temd_set_error(-1, "tracer_epilogue: null argument");
+    if (args->nlev < 2 || args->nlat < 2 || args->nt < 1 || args->ld < (size_t)args->nlat)
+        return temd_set_error(-1, "tracer_epilogue: need nlev >= 2, nlat >= 2, nt >= 1");
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    int rc = launch_tracer_epilogue(*args, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return temd_set_error(rc, "tracer_epilogue: kernel launch failed");
+    return 0;
+}
+
 extern "C" int temd_synth_fields(double* out, int field, int seed, int t0, int nt, int nlev, int ncol, size_t ld,
                                  const double* lat_rad, const double* lon_rad, const double* plev_hpa, void* stream) {
     if (!out || !lat_rad || !lon_rad || !plev_hpa || field < 0 || field > 4 || nt < 1 || nlev < 1 || ncol < 1 || ld < (size_t)ncol)

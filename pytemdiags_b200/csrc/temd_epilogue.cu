@@ -149,6 +149,87 @@ __global__ void k_epi_c(const EpiDev e) {
     OUT(TEMD_OUT_UTENDEPFD)[idx] = epdiv * iacos;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tracer TEM for one tracer (tem_diagnostics.py:602-611, 801-991)
+// ---------------------------------------------------------------------------------------------
+struct TrDev {
+    int nt, nlev, nlat;
+    size_t ld, plane;
+    const double *zmq, *psi, *vtem, *omegatem, *p, *coslat;
+    double* out;
+    Axis ap, al;
+    double p0, a, H;
+};
+#define TOUT(q) (e.out + (size_t)(q) * e.plane)
+enum { TS_MPHICOS = TEMD_NTROUT, TS_MP = TEMD_NTROUT + 1 };
+
+__device__ __forceinline__ bool tr_index(const TrDev& e, int& t, int& k, int& m, size_t& idx) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)e.nt * e.nlev * e.nlat) return false;
+    m = (int)(gid % e.nlat);
+    k = (int)((gid / e.nlat) % e.nlev);
+    t = (int)(gid / ((size_t)e.nlat * e.nlev));
+    idx = ((size_t)t * e.nlev + k) * e.ld + m;
+    return true;
+}
+
+__global__ void k_tr_a(const TrDev e) {
+    int t, k, m; size_t idx;
+    if (!tr_index(e, t, k, m, idx)) return;
+    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
+    const double* qb = e.zmq;
+    const double* qpvpb = e.zmq + e.plane;
+    const double* qpwappb = e.zmq + 2 * e.plane;
+    const double c0 = e.coslat[m], pk = e.p[k];
+    const double acos = e.a * c0, iacos = 1.0 / (e.a * c0);
+    const double dqb_dp = grad3(e.ap, k, qb[up], qb[idx], qb[dn]);                      // :604
+    const double qbc = qb[idx] * c0;                                                  // :606
+    const double qbc_m = (m > 0) ? qb[idx - 1] * e.coslat[m - 1] : qbc;
+    const double qbc_p = (m < e.nlat - 1) ? qb[idx + 1] * e.coslat[m + 1] : qbc;
+    const double dqbc_dlat = grad3(e.al, m, qbc_m, qbc, qbc_p);                       // :608
+    const double psi = e.psi[idx];
+    const double etfy = ((dqb_dp * psi - qpvpb[idx]) * acos) * (pk / e.p0);           // :825-826
+    const double xq = -(dqbc_dlat * iacos);                                           // :859
+    const double etfz = -e.H / e.p0 * ((xq * psi - qpwappb[idx]) * acos);             // :860
+    TOUT(TEMD_TROUT_DQB_DP)[idx] = dqb_dp;
+    TOUT(TEMD_TROUT_QBCOSLAT)[idx] = qbc;
+    TOUT(TEMD_TROUT_DQBCOSLAT_DLAT)[idx] = dqbc_dlat;
+    TOUT(TEMD_TROUT_ETFY)[idx] = etfy;
+    TOUT(TEMD_TROUT_ETFZ)[idx] = etfz;
+    TOUT(TEMD_TROUT_QTENDVTEM)[idx] = -e.vtem[idx] * (dqbc_dlat * iacos);             // :958-959
+    TOUT(TEMD_TROUT_QTENDWTEM)[idx] = -e.omegatem[idx] * dqb_dp;                      // :986-987
+    TOUT(TS_MPHICOS)[idx] = (etfy * (e.p0 / pk)) * c0;                                // :893, :896
+    TOUT(TS_MP)[idx] = etfz * -e.p0 / e.H;                                            // :894
+}
+
+__global__ void k_tr_b(const TrDev e) {
+    int t, k, m; size_t idx;
+    if (!tr_index(e, t, k, m, idx)) return;
+    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
+    const size_t lm = (m > 0) ? idx - 1 : idx, lp = (m < e.nlat - 1) ? idx + 1 : idx;
+    const double* mc = TOUT(TS_MPHICOS);
+    const double* mp = TOUT(TS_MP);
+    const double iacos = 1.0 / (e.a * e.coslat[m]);
+    const double etdiv = grad3(e.al, m, mc[lm], mc[idx], mc[lp]) * iacos + grad3(e.ap, k, mp[up], mp[idx], mp[dn]);   // :897-899
+    TOUT(TEMD_TROUT_ETDIV)[idx] = etdiv;
+    TOUT(TEMD_TROUT_QTENDETFD)[idx] = etdiv * iacos;                                  // :928
+}
+
+int launch_tracer_epilogue(const temd_tracer_args& a, cudaStream_t stream) {
+    TrDev e;
+    e.nt = a.nt; e.nlev = a.nlev; e.nlat = a.nlat; e.ld = a.ld;
+    e.plane = (size_t)a.nt * a.nlev * a.ld;
+    e.zmq = a.zmq; e.psi = a.psi; e.vtem = a.vtem; e.omegatem = a.omegatem; e.p = a.p; e.coslat = a.coslat; e.out = a.out;
+    e.ap = Axis{a.p, a.gp, a.nlev, a.p_uniform, a.hp};
+    e.al = Axis{a.latr, a.gl, a.nlat, a.lat_uniform, a.hlat};
+    e.p0 = a.p0; e.a = a.a; e.H = a.H;
+    const size_t total = (size_t)a.nt * a.nlev * a.nlat;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    k_tr_a<<<blocks, 256, 0, stream>>>(e);
+    k_tr_b<<<blocks, 256, 0, stream>>>(e);
+    return (int)cudaGetLastError();
+}
+
 struct EpilogueArgs { temd_epilogue_args a; };
 
 int launch_tem_epilogue(const EpilogueArgs& wrap, cudaStream_t stream) {

@@ -176,7 +176,30 @@ class Engine:
             rc = self.lib.temd_tem_epilogue(self._plan, C.byref(args), self.stream)
         _lib.check(rc, 'temd_tem_epilogue')
         self._keepalive = d
+        self._epi_full = out          # [nout+2][nt][nlev][Mld] (padded planes, needed by the tracer epilogue)
+        self._epi_consts = (d, p_uni, hp, l_uni, hl, float(p0))
         return {name: out[i, :, :, :self.M] for i, name in enumerate(_lib.EPILOGUE_OUTPUTS)}
+
+    def tracer_epilogue(self, zmq):
+        """zmq: [3][nt][nlev][Mld-strided M] (qb, qpvpb, qpwappb) -> dict of tracer diagnostics.  Must follow
+        tem_epilogue (uses its psi / vtem / omegatem planes)."""
+        nt, nlev = zmq.shape[1], zmq.shape[2]
+        assert zmq.shape[0] == 3 and zmq.stride(2) == self.Mld and zmq.stride(3) == 1
+        d, p_uni, hp, l_uni, hl, p0 = self._epi_consts
+        names = _lib.EPILOGUE_OUTPUTS
+        full = self._epi_full
+        nout = len(_lib.TRACER_OUTPUTS)
+        out = torch.empty((nout + 2, nt, nlev, self.Mld), dtype=torch.float64, device=self.device)
+        args = _lib.TracerArgs(nt=nt, nlev=nlev, nlat=self.M, ld=self.Mld, zmq=zmq.data_ptr(),
+                               psi=full[names.index('psi')].data_ptr(), vtem=full[names.index('vtem')].data_ptr(),
+                               omegatem=full[names.index('omegatem')].data_ptr(), p=d['p'].data_ptr(),
+                               latr=d['latr'].data_ptr(), gp=d['gp'].data_ptr(), gl=d['gl'].data_ptr(),
+                               p_uniform=int(p_uni), lat_uniform=int(l_uni), hp=hp, hlat=hl,
+                               coslat=d['coslat'].data_ptr(), p0=p0, a=a, H=H, out=out.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_tracer_epilogue(self._plan, C.byref(args), self.stream)
+        _lib.check(rc, 'temd_tracer_epilogue')
+        return {name: out[i, :, :, :self.M] for i, name in enumerate(_lib.TRACER_OUTPUTS)}
 
     def synth_fields(self, field, seed, t0, nt, plev_hpa, lat_rad_dev, lon_rad_dev, plev_dev, out=None):
         nlev = plev_dev.shape[0]

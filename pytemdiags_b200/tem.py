@@ -133,11 +133,20 @@ class TEMDiagnostics:
         self.timename = self.dim_names.get('time', DEFAULT_DIMS['time'])
         self.data_dims = (self.ncolname, self.plevname, self.timename)
 
+        # ---- tracers: a single array or a list of arrays (tem_diagnostics.py:282-301)
         if self.q is not None:
-            raise NotImplementedError('tracer inputs (q=) are not implemented in this build yet '
-                                      '(SURVEY.md §8f rank 1); pass q=None')
-        self.ntrac = 0
-        self._q_out_file = []
+            if not isinstance(self.q, (list, tuple)):
+                self.q = [self.q]
+            else:
+                self.q = list(self.q)
+            for qi in self.q:
+                if ar.kind_of(qi) != ar.kind_of(self.ua):
+                    raise RuntimeError('tracers q must be passed as an xarray DataArray, or'
+                                       'a list of xarray DataArrays')
+            self.ntrac = len(self.q)
+        else:
+            self.ntrac = 0
+        self._q_out_file = [None] * self.ntrac
 
         lat = self.lat_native
         lat_np = ar.raw(lat)
@@ -146,6 +155,9 @@ class TEMDiagnostics:
         ncol = lat_np.shape[0]
 
         allvars = {'ua': self.ua, 'va': self.va, 'ta': self.ta, 'wap': self.wap}
+        for i in range(self.ntrac):
+            allvars['q{}'.format(i)] = self.q[i]
+        self._vars = allvars
         self._kind = ar.kind_of(self.ua)
         self._in_dims = {}
         for var, dat in allvars.items():
@@ -250,7 +262,7 @@ class TEMDiagnostics:
     def _slab(self, var, t0, t1, device):
         '''Time steps [t0, t1) of one input as a float64 device tensor [(t1-t0)*K][N] (lev in input order).
         Host arrays are copied with non_blocking=True (a true async DMA when the array is pinned).'''
-        dat = {'ua': self.ua, 'va': self.va, 'ta': self.ta, 'wap': self.wap}[var]
+        dat = self._vars[var]
         r = ar.raw(dat)
         dims = self._in_dims[var]
         if self.timename in dims:
@@ -291,7 +303,11 @@ class TEMDiagnostics:
         budget = self._slab_bytes if self._slab_bytes is not None else ((2 << 30) if on_host else (16 << 30))
         ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
         coef = torch.empty((7, T * K, eng.lpad), dtype=torch.float64, device=dev)
-        names = ('ua', 'va', 'ta', 'wap')
+        ntr = self.ntrac
+        coefq = torch.empty((3 * ntr, T * K, eng.lpad), dtype=torch.float64, device=dev) if ntr else None
+        budget = budget * 4 // (4 + ntr)
+        ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
+        names = ('ua', 'va', 'ta', 'wap') + tuple('q{}'.format(i) for i in range(ntr))
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
@@ -312,27 +328,47 @@ class TEMDiagnostics:
                 main.wait_event(ev)
                 for x in xs:
                     x.record_stream(main)
-                c4 = eng.project(xs, lev_scale=lev_scale, scale_field=2, nlev=K)
+                c4 = eng.project(xs[:4], lev_scale=lev_scale, scale_field=2, nlev=K)
                 cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
                 coef[:4, t0 * K:t1 * K] = c4
                 coef[4:, t0 * K:t1 * K] = cf
+                for i in range(ntr):
+                    # tracer i (tem_diagnostics.py:532-538, 560-570): the fused kernel on (q, v, theta, omega)
+                    # returns q'v' and q'omega' in its first two product slots
+                    cq = eng.project([xs[4 + i]])
+                    c4q = torch.cat([cq, c4[1:]], 0)
+                    cfq = eng.eddy_flux_project(xs[4 + i], xs[1], xs[2], xs[3], c4q, lev_scale, K)
+                    coefq[3 * i, t0 * K:t1 * K] = cq[0]
+                    coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = cfq[:2]
                 del xs
         eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
+        if ntr:
+            eng.check_finite(coefq, 'q')
         if self._flip_lev:
             coef = coef.reshape(7, T, K, eng.lpad).flip(2).reshape(7, T * K, eng.lpad).contiguous()
+            if ntr:
+                coefq = coefq.reshape(3 * ntr, T, K, eng.lpad).flip(2).reshape(3 * ntr, T * K, eng.lpad).contiguous()
         self._coef = coef
         zm = eng.synth_out(coef).reshape(7, T, K, eng.M)
         res = eng.tem_epilogue(zm, self.p, self._f_zm, self._coslat_zm, p0=self.p0)
         self._dev_results = {n: zm[i] for i, n in enumerate(_ZM_NAMES)}
         self._dev_results.update(res)
         self._cache = {}
+        self._dev_tracer = []
+        for i in range(ntr):
+            zmq = eng.synth_out(coefq[3 * i:3 * i + 3]).reshape(3, T, K, eng.M)
+            tr = eng.tracer_epilogue(zmq)
+            tr.update(qb=zmq[0], qpvpb=zmq[1], qpwappb=zmq[2])
+            self._dev_tracer.append(tr)
 
     # ------------------------------------------------------------------
-    def _result(self, name, like=None, cast_like=None):
+    def _result(self, name, like=None, cast_like=None, tracer=None):
         '''(lat, plev, time) array of one result, in the container kind of the inputs.'''
-        if name in self._cache:
-            return self._cache[name]
-        t = self._dev_results[name].permute(2, 1, 0).contiguous()      # [T][K][M] -> (M, K, T)
+        key = name if tracer is None else (name, tracer)
+        if key in self._cache:
+            return self._cache[key]
+        src_dict = self._dev_results if tracer is None else self._dev_tracer[tracer]
+        t = src_dict[name].permute(2, 1, 0).contiguous()               # [T][K][M] -> (M, K, T)
         src = self.ua if cast_like is None else cast_like
         dtype = ar.dtype_of(src)
         r = ar.raw(src)
@@ -341,8 +377,57 @@ class TEMDiagnostics:
         if self._kind == 'dataarray':
             coords = {'lat': self._lat_zm, self.plevname: self.plev, self.timename: self.time}
             out = ar.make_dataarray(self.ua, out, ('lat', self.plevname, self.timename), coords=coords, name=name)
-        self._cache[name] = out
+        self._cache[key] = out
         return out
+
+    def _qi(self, qi, who):
+        '''tracer-index convention of the reference (e.g. tem_diagnostics.py:814-816)'''
+        if qi is None and self.ntrac == 1:
+            return 0
+        if qi is None and self.ntrac > 1:
+            raise RuntimeError('qi must be passed to {}() when len(q) > 1!'.format(who))
+        if self.ntrac == 0:
+            raise RuntimeError('{}() needs tracers: pass q= to TEMDiagnostics'.format(who))
+        return qi
+
+    def _tracer(self, name, qi, who=None):
+        qi = self._qi(qi, who or name)
+        return self._result(name, cast_like=self.q[qi], tracer=qi)
+
+    def _tracer_list(self, name):
+        return [self._result(name, cast_like=self.q[i], tracer=i) for i in range(self.ntrac)]
+
+    # tracer intermediates (tem_diagnostics.py:458-475): lists, one entry per tracer
+    qb = property(lambda self: self._tracer_list('qb'))
+    qpvpb = property(lambda self: self._tracer_list('qpvpb'))
+    qpwappb = property(lambda self: self._tracer_list('qpwappb'))
+    dqb_dp = property(lambda self: self._tracer_list('dqb_dp'))
+    qbcoslat = property(lambda self: self._tracer_list('qbcoslat'))
+    dqbcoslat_dlat = property(lambda self: self._tracer_list('dqbcoslat_dlat'))
+
+    def etfy(self, qi=None):
+        '''northward eddy tracer flux (tem_diagnostics.py:801-832)'''
+        return self._tracer('etfy', qi)
+
+    def etfz(self, qi=None):
+        '''upward eddy tracer flux (tem_diagnostics.py:836-866)'''
+        return self._tracer('etfz', qi)
+
+    def etdiv(self, qi=None):
+        '''eddy tracer flux divergence (tem_diagnostics.py:870-905)'''
+        return self._tracer('etdiv', qi)
+
+    def qtendetfd(self, qi=None):
+        '''tracer tendency due to eddy tracer flux divergence (tem_diagnostics.py:909-934)'''
+        return self._tracer('qtendetfd', qi)
+
+    def qtendvtem(self, qi=None):
+        '''tracer tendency due to TEM northward advection (tem_diagnostics.py:938-965)'''
+        return self._tracer('qtendvtem', qi)
+
+    def qtendwtem(self, qi=None):
+        '''tracer tendency due to TEM upward advection (tem_diagnostics.py:969-991)'''
+        return self._tracer('qtendwtem', qi)
 
     # zonal means and derived intermediates (tem_diagnostics.py:412-457)
     ub = property(lambda self: self._result('ub'))

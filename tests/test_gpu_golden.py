@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, 'golden'))
-GOLDEN = sorted(glob.glob(os.path.join(HERE, 'golden', '*.npz')))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, 'golden', 'tem_*.npz')))
 TOL = 1e-10
 METHODS = ('vtem', 'omegatem', 'wtem', 'psitem', 'epfy', 'epfz', 'epdiv', 'utendepfd', 'utendvtem', 'utendwtem')
 PROPS = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb', 'dub_dp', 'dthetab_dp', 'ubcoslat',
@@ -31,6 +31,8 @@ def test_tem_against_reference_outputs(path):
     da = {n: DataArray(g['in_' + n], dims=dims, coords=coords, name=n) for n in ('ua', 'va', 'ta', 'wap')}
     lat = DataArray(g['lat'], dims=('ncol',), name='lat')
     kw = {} if float(g['zm_dlat']) == 1 else {'zm_dlat': int(g['zm_dlat'])}
+    if 'in_q' in g:
+        kw['q'] = DataArray(g['in_q'], dims=dims, coords=coords, name='q')
     tem = TEMDiagnostics(da['ua'], da['va'], da['ta'], da['wap'], lat, L=int(g['L']), debug_level=0, **kw)
     for m in METHODS:
         r = getattr(tem, m)()
@@ -40,6 +42,13 @@ def test_tem_against_reference_outputs(path):
         assert nerr(r.values, g['ref_' + m]) < TOL, (m, nerr(r.values, g['ref_' + m]))
     for p_ in PROPS:
         assert nerr(getattr(tem, p_).values, g['ref_' + p_]) < TOL, p_
+    if 'in_q' in g:     # tracer TEM (tem_diagnostics.py:801-991)
+        for m in ('etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem'):
+            r = getattr(tem, m)()
+            assert r.dims == ('lat', 'plev', 'time') and r.name == m
+            assert nerr(r.values, g['ref_' + m + '0']) < TOL, (m, nerr(r.values, g['ref_' + m + '0']))
+        for p_ in ('qb', 'qpvpb', 'qpwappb', 'dqb_dp', 'qbcoslat', 'dqbcoslat_dlat'):
+            assert nerr(getattr(tem, p_)[0].values, g['ref_' + p_ + '0']) < TOL, p_
     # the stand-alone averager on the same grid (sph_zonal_mean.py:285-296)
     A = da['ua'].transpose('ncol', 'plev', 'time')
     zm = tem.ZM.sph_zonal_mean(A)

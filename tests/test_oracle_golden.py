@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.npz')))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'tem_*.npz')))
 TRACER = ('etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem', 'qb', 'qpvpb', 'qpwappb', 'dqb_dp',
           'qbcoslat', 'dqbcoslat_dlat')
 
