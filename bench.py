@@ -20,6 +20,11 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the reference arm uses every host core (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -91,6 +96,11 @@ def cpu_suite_sample(cfg, L, tsample, seed=0, repeat=1):
     """Times the oracle port (factored form) on `tsample` time steps of the workload.  Returns
     (points per second, seconds per suite, setup seconds, threads)."""
     import oracle
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     from pytemdiags_b200 import synthetic as syn
     lat, lon = syn.make_grid(cfg['grid'])
     plev = syn.default_plev(cfg['K'])
@@ -309,6 +319,14 @@ def run_ours(args):
                            'this pool (profiles/r01_microbench_fp64.log), nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2',
             'algorithmic_flops_per_launch': fl_eddy}
     roof['frac'] = roof['achieved'] / roof['peak']
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('%s:%d' % (args.config, Ts))
+        if tr:
+            roof['traffic'] = tr['k_eddy']['dram_bytes']
+            roof['traffic_unit'] = 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)'
+            roof['algorithmic_bytes_per_launch'] = 32.0 * N * rows
+    except Exception:
+        pass
     roof_proj = {'bound': 'tensor', 'kernel': 'k_project (temd_project)',
                  'achieved': fl_proj / (kms['project'] * 1e-3) / 1e12, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s'}
     roof_proj['frac'] = roof_proj['achieved'] / roof_proj['peak']
@@ -316,7 +334,7 @@ def run_ours(args):
     hbm = {'bytes_per_point': 64, 'achieved_gbs': 64.0 * N * rows / (ms * 1e-3) / 1e9, 'peak_gbs': pk.get('hbm_gbs')}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         v, secs, setup, cores = cpu_suite_sample(cfg, L, args.cpu_tsample)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': '%d of %d time steps of %s, factored NumPy oracle (literal N x N form infeasible: %.0f GB); '

@@ -41,6 +41,11 @@ int temd_plan_lpad(const temd_plan* plan);
  * written to host memory if sanity_host != NULL. */
 int temd_basis_build(temd_plan* plan, const double* x, const double* x_out, double* sanity_host, void* stream);
 
+/* Deprecated quadrature inverse of the reference, Y0inv = Y0^T diag(w) (sph_zonal_mean.py:72,180-181,383-386):
+ * w[N] are the grid-cell area weights ALREADY multiplied by 4 pi.  temd_project / temd_synth_* then compute
+ * Y (Y0^T diag(w)) A; temd_eddy_flux_project is not available in this mode. */
+int temd_basis_build_weighted(temd_plan* plan, const double* x, const double* x_out, const double* w, void* stream);
+
 /* Dense exports of the reference's attributes Y0 [N][L+1], Y0inv [L+1][N], Y0p [M][L+1]
  * (sph_zonal_mean.py:420-422); any pointer may be NULL. */
 int temd_basis_export(temd_plan* plan, double* Y0, double* Y0inv, double* Y0p, void* stream);

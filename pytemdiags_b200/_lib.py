@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libtemd.so')
 # every symbol include/temd.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
-    'temd_basis_build', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
+    'temd_basis_build', 'temd_basis_build_weighted', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
     'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_synth_fields',
 )
 
@@ -64,6 +64,7 @@ def load():
     lib.temd_plan_destroy.argtypes = [vp]
     lib.temd_plan_lpad.argtypes = [vp]
     lib.temd_basis_build.argtypes = [vp, vp, vp, C.POINTER(d), vp]
+    lib.temd_basis_build_weighted.argtypes = [vp, vp, vp, vp, vp]
     lib.temd_basis_export.argtypes = [vp, vp, vp, vp, vp]
     lib.temd_project.argtypes = [vp, C.POINTER(vp), i, i, sz, vp, i, i, vp, vp]
     lib.temd_synth_out.argtypes = [vp, vp, i, vp, sz, vp]

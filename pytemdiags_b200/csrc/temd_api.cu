@@ -94,6 +94,15 @@ __global__ void k_trace_offdiag(const double* __restrict__ G, int n, int ld, dou
     if (threadIdx.x == 0) { out2[0] = s_tr[0]; out2[1] = s_off[0]; }
 }
 
+// out[l][n] = in[l][n] * w[n]   (Y0inv = Y0^T diag(w), reference sph_zonal_mean.py:383-386)
+__global__ void k_scale_cols(const double* __restrict__ in, const double* __restrict__ w, double* __restrict__ out,
+                             int rows, int n, size_t ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (i >= ld || l >= rows) return;
+    out[(size_t)l * ld + i] = (i < (size_t)n) ? in[(size_t)l * ld + i] * w[i] : 0.0;
+}
+
 // out[i][j] = in[j][i]; in is [rows_in][ld_in], out is [cols_in][ld_out]  (dense exports only)
 __global__ void k_transpose(const double* __restrict__ in, int rows_in, int cols_in, size_t ld_in,
                             double* __restrict__ out, size_t ld_out) {
@@ -127,6 +136,7 @@ struct temd_plan {
     int* status;
     double* sanity;
     bool built;
+    bool weighted;   // deprecated quadrature inverse Y0inv = Y0^T diag(w): qt = raw basis (synthesis), qt_alt = weighted (projection)
 };
 
 static int ensure_work(temd_plan* p, size_t doubles) {
@@ -257,6 +267,36 @@ extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_o
     }
     TEMD_CUDA(cudaStreamSynchronize(st));
     p->built = true;
+    p->weighted = false;
+    return 0;
+}
+
+extern "C" int temd_basis_build_weighted(temd_plan* p, const double* x, const double* x_out, const double* w, void* stream) {
+    if (p == nullptr || x == nullptr || x_out == nullptr || w == nullptr) return temd_set_error(-1, "basis_build_weighted: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    std::vector<double> ra(p->lpad, 0.0), rb(p->lpad, 0.0);
+    const double PI = 3.141592653589793238462643383279502884;
+    ra[0] = std::sqrt(1.0 / (4.0 * PI));
+    if (p->L >= 1) ra[1] = std::sqrt(3.0 / (4.0 * PI));
+    for (int l = 2; l <= p->L; l++) {
+        ra[l] = std::sqrt(4.0 * l * l - 1.0) / l;
+        rb[l] = ((l - 1.0) / l) * std::sqrt((2.0 * l + 1.0) / (2.0 * l - 3.0));
+    }
+    TEMD_CUDA(cudaMemcpyAsync(p->rec_a, ra.data(), p->lpad * sizeof(double), cudaMemcpyHostToDevice, st));
+    TEMD_CUDA(cudaMemcpyAsync(p->rec_b, rb.data(), p->lpad * sizeof(double), cudaMemcpyHostToDevice, st));
+    TEMD_CUDA(cudaStreamSynchronize(st));
+    TEMD_CUDA(cudaMemcpyAsync(p->x, x, p->N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TEMD_CUDA(cudaMemcpyAsync(p->x_out, x_out, p->M * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc;
+    if ((rc = launch_basis(p->x, p->N, p->L, p->rec_a, p->rec_b, p->qt, p->ld_q, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+    if ((rc = launch_basis(p->x_out, p->M, p->L, p->rec_a, p->rec_b, p->qpt, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+    dim3 grid((unsigned)((p->ld_q + 255) / 256), p->lpad);
+    k_scale_cols<<<grid, 256, 0, st>>>(p->qt, w, p->qt_alt, p->lpad, p->N, p->ld_q);
+    TEMD_CUDA(cudaGetLastError());
+    TEMD_CUDA(cudaStreamSynchronize(st));
+    p->built = true;
+    p->weighted = true;
     return 0;
 }
 
@@ -266,6 +306,21 @@ extern "C" int temd_basis_export(temd_plan* p, double* Y0, double* Y0inv, double
     TEMD_CUDA(cudaSetDevice(p->dev));
     int rc;
     dim3 tb(32, 8);
+    if (p->weighted) {
+        if (Y0 != nullptr) {
+            dim3 grid((p->N + 31) / 32, (p->Lp + 31) / 32);
+            k_transpose<<<grid, tb, 0, st>>>(p->qt, p->Lp, p->N, p->ld_q, Y0, p->Lp);
+        }
+        if (Y0p != nullptr) {
+            dim3 grid((p->M + 31) / 32, (p->Lp + 31) / 32);
+            k_transpose<<<grid, tb, 0, st>>>(p->qpt, p->Lp, p->M, p->ld_p, Y0p, p->Lp);
+        }
+        if (Y0inv != nullptr)
+            TEMD_CUDA(cudaMemcpy2DAsync(Y0inv, (size_t)p->N * sizeof(double), p->qt_alt, p->ld_q * sizeof(double),
+                                        (size_t)p->N * sizeof(double), p->Lp, cudaMemcpyDeviceToDevice, st));
+        TEMD_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (Y0 != nullptr) {
         if ((rc = launch_basis(p->x, p->N, p->L, p->rec_a, p->rec_b, p->qt_alt, p->ld_q, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
         dim3 grid((p->N + 31) / 32, (p->Lp + 31) / 32);
@@ -303,7 +358,7 @@ extern "C" int temd_project(temd_plan* p, const double* const* fields_host, int 
     const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 64);
     int rc = ensure_work(p, project_workspace_doubles(nfields, rows, p->lpad, nsplit));
     if (rc) return rc;
-    return launch_project(fields_host, nfields, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef, p->work, nsplit,
+    return launch_project(fields_host, nfields, rows, p->N, ld, p->weighted ? p->qt_alt : p->qt, p->lpad, p->ld_q, coef, p->work, nsplit,
                           lev_scale, scale_field, nlev < 1 ? 1 : nlev, st);
 }
 
@@ -346,6 +401,7 @@ extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const doubl
     if (!u || !v || !t || !w || !coef4 || !coef_flux || rows < 1 || ld < (size_t)p->N)
         return temd_set_error(-1, "eddy_flux_project: bad arguments");
     if (!eddy_supported(p->lpad)) return temd_set_error(-1, "eddy_flux_project: L = %d too large for the fused kernel (max 407)", p->L);
+    if (p->weighted) return temd_set_error(-1, "eddy_flux_project: not available with the quadrature-weights inverse (TEMDiagnostics never uses it)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TEMD_CUDA(cudaSetDevice(p->dev));
     const int nchunks = (p->N + 15) / 16;

@@ -16,6 +16,7 @@
 // C_f lives in shared memory for the CTA's lifetime (row-major, row stride = 4 or 12 mod 16
 // doubles so that the GEMM1 A fragments are bank-conflict-free under the mnmajor_k permutation).
 #include <cstdlib>
+#include <type_traits>
 
 #include "temd_common.cuh"
 #include "temd_internal.h"
@@ -37,6 +38,7 @@ struct EddyParams {
     int stages;
     int nlev;
     int qbox;          // rows per QT TMA box (divides lpad, <= 256)
+    int nch;           // chunks per barrier round (2 needs >= 4 pipeline stages)
     const double* coef4;      // [4][rows][lpad]
     const double* lev_scale;  // [nlev] or null
     double* part;             // [nsplit][3][rows][lpad]
@@ -181,63 +183,88 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     const uint32_t e_row_off = (uint32_t)((mi * 8 + g) * TILE_ROW_BYTES);
     const uint32_t q_off = 4 * XF_BYTES;
 
-    for (int i = 0; i < nloc; i++) {
-        const int s = i % STAGES;
-        mbar_wait(full_bar(s), (i / STAGES) & 1);
-        const uint32_t st = smem_base + s * stage_bytes;
-        const uint32_t qs = st + q_off;
-
+    // One barrier round handles NCH consecutive chunks (pipeline stages): GEMM1 of all of them (sharing the
+    // coefficient fragments), their eddies, ONE group barrier, then GEMM2 of all of them.
+    auto round = [&](auto nch_tag, int i) {
+        constexpr int NCH = decltype(nch_tag)::value;
+        uint32_t st[NCH], qs[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int s = (i + c) % STAGES;
+            mbar_wait(full_bar(s), ((i + c) / STAGES) & 1);
+            st[c] = smem_base + s * stage_bytes;
+            qs[c] = st[c] + q_off;
+        }
         // ---------------- GEMM1: S = C * QT (contraction over l = QT tile rows) ----------------
-        double sacc[NF1][NN1][2];
+        double sacc[NCH][NF1][NN1][2];
 #pragma unroll
-        for (int ff = 0; ff < NF1; ff++)
+        for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int nn = 0; nn < NN1; nn++) sacc[ff][nn][0] = sacc[ff][nn][1] = 0.0;
+            for (int ff = 0; ff < NF1; ff++)
+#pragma unroll
+                for (int nn = 0; nn < NN1; nn++) sacc[c][ff][nn][0] = sacc[c][ff][nn][1] = 0.0;
 #pragma unroll 2
         for (int l8 = 0; l8 < p.nt; l8++) {
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int kin = c ? k1c1 : k1c0;           // row inside the 8-row group
+            for (int cc = 0; cc < 2; cc++) {
+                const int kin = cc ? k1c1 : k1c0;           // row inside the 8-row group
                 const int k = l8 * 8 + kin;
-                double a[NF1], b[NN1];
+                double a[NF1], b[NCH][NN1];
 #pragma unroll
                 for (int ff = 0; ff < NF1; ff++) a[ff] = lds64(a1_off[ff] + (uint32_t)k * 8u);
 #pragma unroll
-                for (int nn = 0; nn < NN1; nn++) {
-                    const int jn = jn1 + nn;
-                    b[nn] = lds64(qs + (uint32_t)k * TILE_ROW_BYTES + (uint32_t)((((jn * 4 + (g >> 1)) ^ kin) & 7) << 4) + (uint32_t)((g & 1) << 3));
-                }
+                for (int c = 0; c < NCH; c++)
 #pragma unroll
-                for (int ff = 0; ff < NF1; ff++)
+                    for (int nn = 0; nn < NN1; nn++) {
+                        const int jn = jn1 + nn;
+                        b[c][nn] = lds64(qs[c] + (uint32_t)k * TILE_ROW_BYTES + (uint32_t)((((jn * 4 + (g >> 1)) ^ kin) & 7) << 4) + (uint32_t)((g & 1) << 3));
+                    }
 #pragma unroll
-                    for (int nn = 0; nn < NN1; nn++) dmma(sacc[ff][nn][0], sacc[ff][nn][1], a[ff], b[nn]);
+                for (int c = 0; c < NCH; c++)
+#pragma unroll
+                    for (int ff = 0; ff < NF1; ff++)
+#pragma unroll
+                        for (int nn = 0; nn < NN1; nn++) dmma(sacc[c][ff][nn][0], sacc[c][ff][nn][1], a[ff], b[c][nn]);
             }
         }
         // ---------------- eddies, in place over the X tiles ----------------
 #pragma unroll
-        for (int ff = 0; ff < NF1; ff++) {
-            const int f = f1 + ff;
-            const double sc = (f == 2) ? tscale : 1.0;
+        for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int nn = 0; nn < NN1; nn++) {
-                const int row = mi * 8 + g;
-                const int col = (jn1 + nn) * 8 + 2 * t;
-                const uint32_t addr = st + f * XF_BYTES + swz_off(row, col);
-                const double2 x = lds128(addr);
-                sts128(addr, sc * x.x - sacc[ff][nn][0], sc * x.y - sacc[ff][nn][1]);
+            for (int ff = 0; ff < NF1; ff++) {
+                const int f = f1 + ff;
+                const double sc = (f == 2) ? tscale : 1.0;
+#pragma unroll
+                for (int nn = 0; nn < NN1; nn++) {
+                    const int row = mi * 8 + g;
+                    const int col = (jn1 + nn) * 8 + 2 * t;
+                    const uint32_t addr = st[c] + f * XF_BYTES + swz_off(row, col);
+                    const double2 x = lds128(addr);
+                    sts128(addr, sc * x.x - sacc[c][ff][nn][0], sc * x.y - sacc[c][ff][nn][1]);
+                }
             }
-        }
         named_bar_sync(grp_bar, grp_threads);
 
         // ---------------- GEMM2: acc += (E_a .* E_b) * QT^T (contraction over the 16 columns) ----------------
-        if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES>(acc, st, qs, e_row_off, coff2, g, j_begin);
-        else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES>(acc, st, qs, e_row_off, coff2, g, j_begin);
-
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
+            else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
+        }
         // the E tiles were written through the generic proxy; order them before the next TMA refill
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(s));
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) mbar_arrive(empty_bar((i + c) % STAGES));
+        }
+    };
+
+    int i = 0;
+    if (p.nch == 2) {
+        for (; i + 2 <= nloc; i += 2) round(std::integral_constant<int, 2>{}, i);
     }
+    for (; i < nloc; i++) round(std::integral_constant<int, 1>{}, i);
 
     // ------------------------------ split-K partials ------------------------------
     const int row = row0 + mi * 8 + g;
@@ -311,6 +338,8 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     int smem;
     p.stages = eddy_stages(nt, bm, &smem);
     if (p.stages < 2) return temd_set_error(-1, "eddy_flux_project: not enough shared memory for lpad = %d", lpad);
+    p.nch = (p.stages >= 4) ? 2 : 1;
+    { const char* e = getenv("TEMD_EDDY_NCH"); if (e && atoi(e) == 1) p.nch = 1; }
     // 16 consumer warps (4 per SM sub-partition) hide the per-chunk phase changes better than 8; the
     // BM = 8 layout has only 8 GEMM1 units per chunk, so it stays at 8 warps.
     int warps = (bm == 8) ? 8 : 16;

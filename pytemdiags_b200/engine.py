@@ -71,10 +71,18 @@ class Engine:
         return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
 
     # ---- sph_compute_matrices (sph_zonal_mean.py:302-422) ----
-    def build_basis(self, sanity=False):
+    def build_basis(self, sanity=False, weights=None):
         # x = cos(colatitude), computed exactly like the reference: coalt = deg2rad(90 - lat)
         x = self._dev(np.cos(np.deg2rad(90 - self.lat)))
         x_out = self._dev(np.cos(np.deg2rad(90 - self.lat_out)))
+        if weights is not None:
+            # deprecated reference path: Y0inv = Y0^T diag(4 pi w)  (sph_zonal_mean.py:180-181,383-386)
+            w = self._dev(4 * np.pi * np.asarray(weights, dtype=np.float64))
+            with torch.cuda.device(self.device):
+                rc = self.lib.temd_basis_build_weighted(self._plan, _ptr(x), _ptr(x_out), _ptr(w), self.stream)
+            _lib.check(rc, 'temd_basis_build_weighted')
+            self.built = True
+            return self
         san = (C.c_double * 2)()
         with torch.cuda.device(self.device):
             rc = self.lib.temd_basis_build(self._plan, _ptr(x), _ptr(x_out), san if sanity else None, self.stream)

@@ -16,10 +16,11 @@ _ENGINE_CACHE = {}
 _ENGINE_CACHE_MAX = 2
 
 
-def _cached_engine(lat, lat_out, L, device, overwrite=False):
+def _cached_engine(lat, lat_out, L, device, overwrite=False, weights=None):
     import hashlib
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-    key = (hashlib.sha1(lat.tobytes()).hexdigest(), hashlib.sha1(lat_out.tobytes()).hexdigest(), int(L), str(dev))
+    wkey = None if weights is None else hashlib.sha1(np.ascontiguousarray(weights, dtype=np.float64).tobytes()).hexdigest()
+    key = (hashlib.sha1(lat.tobytes()).hexdigest(), hashlib.sha1(lat_out.tobytes()).hexdigest(), int(L), str(dev), wkey)
     if overwrite:
         _ENGINE_CACHE.pop(key, None)
     eng = _ENGINE_CACHE.get(key)
@@ -42,9 +43,10 @@ class sph_zonal_averager:
         Zonal averages of fields on unstructured grids by spherical-harmonic (m=0) least squares.
 
         Parameters follow the reference (sph_zonal_mean.py:36-37): `lat` native latitudes [deg] (N),
-        `lat_out` output latitudes [deg] (M), `L` maximum degree.  `weights` selects the reference's
-        deprecated quadrature inverse Y0inv = Y0^T diag(4 pi w) (sph_zonal_mean.py:72,383-386), which
-        this build does not implement (raises).  `grid_name`, `grid_out_name`, `overwrite`,
+        `lat_out` output latitudes [deg] (M), `L` maximum degree.  `weights` (grid-cell area weights summing
+        to 1) selects the reference's deprecated quadrature inverse Y0inv = Y0^T diag(4 pi w)
+        (sph_zonal_mean.py:72,180-181,383-386); unlike the reference the caller's array is not scaled in
+        place.  `grid_name`, `grid_out_name`, `overwrite`,
         `save_dest` only name cache files in the reference and are ignored.  `device`: CUDA device.
         '''
         self.L = L
@@ -61,8 +63,9 @@ class sph_zonal_averager:
         self.debug = debug
         self.logfile = logfile
         if weights is not None:
-            raise NotImplementedError('the deprecated weights= path of the reference (Y0inv = Y0^T diag(w)) is not '
-                                      'implemented; pass weights=None for the least-squares inverse')
+            self.weights = np.asarray(weights.values if ar.is_dataarray(weights) else weights, dtype=np.float64)
+            if len(self.weights) != len(self.lat):
+                raise RuntimeError('number of weights must equal number of native grid latitudes!')
         self.N = len(self.lat)
         self.M = len(self.lat_out)
         self.l = np.arange(self.L + 1)
@@ -76,7 +79,7 @@ class sph_zonal_averager:
         self.Y0p_file_out = None
         if not torch.cuda.is_available():
             raise RuntimeError('pytemdiags_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
-        self._engine = _cached_engine(self.lat, self.lat_out, self.L, device, overwrite=overwrite)
+        self._engine = _cached_engine(self.lat, self.lat_out, self.L, device, overwrite=overwrite, weights=self.weights)
         self._mats = None
 
     # ------------------------------------------------------------------
@@ -87,9 +90,9 @@ class sph_zonal_averager:
             return
         if self._engine.built and not overwrite:
             return                                   # "read from the cache" (sph_zonal_mean.py:330-345)
-        self._engine.build_basis(sanity=bool(self.debug))
+        self._engine.build_basis(sanity=bool(self.debug) and self.weights is None, weights=self.weights)
         self._mats = None
-        if self.debug:
+        if self.debug and self.weights is None:
             print('(sph_zonal_mean debug) Sanity check: sum(diag(Q^T Q)) = {} (should be {}); '
                   'sum(offdiag) = {} (should be zero)'.format(self._engine.sanity[0], self.L + 1,
                                                               self._engine.sanity[1]))

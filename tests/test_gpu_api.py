@@ -144,3 +144,22 @@ def test_error_behaviour():
     x = np.zeros(lat.shape[0]); x[5] = np.nan
     with pytest.raises(RuntimeError, match='nans'):
         ZM.sph_zonal_mean(x)
+
+
+def test_zonal_averager_weights_path():
+    """Deprecated quadrature inverse Y0inv = Y0^T diag(4 pi w) (sph_zonal_mean.py:180-181,383-386)."""
+    from pytemdiags_b200 import sph_zonal_averager
+    lat, lon = syn.pg2_grid(10)
+    lat_out = np.arange(-89.5, 90.5, 1)
+    w = np.cos(np.deg2rad(lat)); w /= w.sum()
+    w0 = w.copy()
+    ZM = sph_zonal_averager(lat, lat_out, 20, weights=w)
+    ZM.sph_compute_matrices()
+    assert np.array_equal(w, w0)
+    Y0 = oracle.sph_basis(lat, 20)
+    Y0p = oracle.sph_basis(lat_out, 20)
+    Y0inv = np.matmul(Y0.T, np.diag(4 * np.pi * w))
+    A = np.random.default_rng(1).standard_normal((lat.shape[0], 4, 2))
+    assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < TOL
+    assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < TOL
+    assert nerr(ZM.Y0inv, Y0inv) < 1e-13 and nerr(ZM.Y0, Y0) < 1e-12
