@@ -370,7 +370,7 @@ def main():
     ap.add_argument('--config', default='config2')
     ap.add_argument('--slab-steps', type=int, default=73)
     ap.add_argument('--e2e-steps', type=int, default=16)
-    ap.add_argument('--cpu-tsample', type=int, default=2)
+    ap.add_argument('--cpu-tsample', type=int, default=8)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

@@ -62,6 +62,16 @@ int temd_synth_out(temd_plan* plan, const double* coef, int rows, double* out, s
 /* sph_zonal_mean_native (sph_zonal_mean.py:285-290): out[row][n] on the native columns. */
 int temd_synth_native(temd_plan* plan, const double* coef, int rows, double* out, size_t ld_out, void* stream);
 
+/* On-demand native-grid eddy field of the reference's properties up, vp, thetap, wapp, qp
+ * (tem_diagnostics.py:517-529,537): out[row][n] = lev_scale[row % nlev] * x[row][n] - (Q coef)[row][n]
+ * (lev_scale NULL = 1).  Not on the hot path: the fused kernel below never materialises these. */
+int temd_eddy_native(temd_plan* plan, const double* x, size_t ld_x, const double* coef, int rows,
+                     const double* lev_scale, int nlev, double* out, size_t ld_out, void* stream);
+
+/* Element-wise product out = a .* b on [rows][ncol] arrays (properties upvp, upwapp, vptp, :547-555). */
+int temd_multiply(const double* a, size_t ld_a, const double* b, size_t ld_b, double* out, size_t ld_out,
+                  int rows, int ncol, void* stream);
+
 /* _decompose_zm_eddy + _compute_fluxes (tem_diagnostics.py:510-558), fused: per column tile forms the
  * native zonal means of u, v, T, omega from coef4 ([4][rows][lpad], order u,v,T,omega, T unscaled),
  * the eddies, the products u'v', u'omega', v'T' and projects them: coef_flux [3][rows][lpad]

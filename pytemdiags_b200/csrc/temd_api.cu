@@ -94,6 +94,25 @@ __global__ void k_trace_offdiag(const double* __restrict__ G, int n, int ld, dou
     if (threadIdx.x == 0) { out2[0] = s_tr[0]; out2[1] = s_off[0]; }
 }
 
+// out[row][n] = scale[row % nlev] * x[row][n] - out[row][n]   (eddy X' = X - zonal mean; scale = theta factor or null)
+__global__ void k_eddy_native(const double* __restrict__ x, size_t ld_x, const double* __restrict__ scale, int nlev,
+                              double* __restrict__ out, size_t ld_out, int rows, int n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= (size_t)n || r >= rows) return;
+    const double s = scale ? scale[r % nlev] : 1.0;
+    out[(size_t)r * ld_out + i] = s * x[(size_t)r * ld_x + i] - out[(size_t)r * ld_out + i];
+}
+
+// out = a .* b
+__global__ void k_mul(const double* __restrict__ a, size_t ld_a, const double* __restrict__ b, size_t ld_b,
+                      double* __restrict__ out, size_t ld_out, int rows, int n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= (size_t)n || r >= rows) return;
+    out[(size_t)r * ld_out + i] = a[(size_t)r * ld_a + i] * b[(size_t)r * ld_b + i];
+}
+
 // out[l][n] = in[l][n] * w[n]   (Y0inv = Y0^T diag(w), reference sph_zonal_mean.py:383-386)
 __global__ void k_scale_cols(const double* __restrict__ in, const double* __restrict__ w, double* __restrict__ out,
                              int rows, int n, size_t ld) {
@@ -378,15 +397,19 @@ extern "C" int temd_synth_native(temd_plan* p, const double* coef, int rows, dou
 
 extern "C" int temd_check_finite(const double* data, size_t n, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int* flag = nullptr;
-    TEMD_CUDA(cudaMalloc(&flag, sizeof(int)));
-    cudaMemsetAsync(flag, 0, sizeof(int), st);
+    // one persistent 4-byte flag per device (never freed: cudaFree would synchronise the whole device)
+    static int* flags[64] = {nullptr};
+    int dev = 0;
+    TEMD_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return temd_set_error(-1, "check_finite: device index out of range");
+    if (flags[dev] == nullptr) TEMD_CUDA(cudaMalloc(&flags[dev], sizeof(int)));
+    int* flag = flags[dev];
+    TEMD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 1184);
     k_check_finite<<<blocks ? blocks : 1, 256, 0, st>>>(data, n, flag);
     int h = 0;
     cudaError_t e = cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(flag);
     if (e != cudaSuccess) return temd_set_error((int)e, "check_finite: %s", cudaGetErrorString(e));
     if (h) return temd_set_error(-2, "non-finite values (NaN/Inf) found");
     return 0;
@@ -422,6 +445,29 @@ extern "C" int temd_tem_epilogue(temd_plan* p, const temd_epilogue_args* args, v
     w.a = *args;
     int rc = launch_tem_epilogue(w, reinterpret_cast<cudaStream_t>(stream));
     if (rc) return temd_set_error(rc, "tem_epilogue: kernel launch failed");
+    return 0;
+}
+
+extern "C" int temd_eddy_native(temd_plan* p, const double* x, size_t ld_x, const double* coef, int rows,
+                                const double* lev_scale, int nlev, double* out, size_t ld_out, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "eddy_native: basis not built");
+    if (!x || !coef || !out || rows < 1 || ld_x < (size_t)p->N || ld_out < (size_t)p->N) return temd_set_error(-1, "eddy_native: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_CUDA(cudaSetDevice(p->dev));
+    int rc = launch_synth(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, st);
+    if (rc) return rc;
+    dim3 grid((p->N + 255) / 256, rows);
+    k_eddy_native<<<grid, 256, 0, st>>>(x, ld_x, lev_scale, nlev < 1 ? 1 : nlev, out, ld_out, rows, p->N);
+    TEMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int temd_multiply(const double* a, size_t ld_a, const double* b, size_t ld_b, double* out, size_t ld_out,
+                             int rows, int ncol, void* stream) {
+    if (!a || !b || !out || rows < 1 || ncol < 1) return temd_set_error(-1, "multiply: bad arguments");
+    dim3 grid((ncol + 255) / 256, rows);
+    k_mul<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, ld_a, b, ld_b, out, ld_out, rows, ncol);
+    TEMD_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -144,6 +144,27 @@ class Engine:
         _lib.check(rc, 'temd_synth_native')
         return out[:, :self.N]
 
+    def eddy_native(self, x, coef, lev_scale=None, nlev=1):
+        """x: [rows][N] field, coef: [rows][lpad] -> eddy field [rows][N] (on-demand properties only)."""
+        self._check_field(x)
+        rows = x.shape[0]
+        ld = self.N + (self.N & 1)
+        out = torch.empty((rows, ld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_eddy_native(self._plan, _ptr(x), x.stride(0), _ptr(coef), rows, _ptr(lev_scale), nlev,
+                                           _ptr(out), ld, self.stream)
+        _lib.check(rc, 'temd_eddy_native')
+        return out[:, :self.N]
+
+    def multiply(self, a_, b_):
+        rows, n = a_.shape
+        out = torch.empty((rows, n + (n & 1)), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_multiply(_ptr(a_), a_.stride(0), _ptr(b_), b_.stride(0), _ptr(out), out.stride(0), rows, n,
+                                        self.stream)
+        _lib.check(rc, 'temd_multiply')
+        return out[:, :n]
+
     def check_finite(self, t, what='input'):
         rc = self.lib.temd_check_finite(_ptr(t), t.numel(), self.stream)
         if rc == -2:
@@ -168,11 +189,21 @@ class Engine:
         coefficient block).  Returns dict name -> [nt][nlev][M] device tensors."""
         nt, nlev = zm.shape[1], zm.shape[2]
         assert zm.shape[0] == 7 and zm.shape[3] == self.M and zm.stride(2) == self.Mld and zm.stride(3) == 1
-        latr = np.deg2rad(self.lat_out)
-        gp, p_uni, hp = gradient_coefficients(p_pa)
-        gl, l_uni, hl = gradient_coefficients(latr)
-        d = dict(p=self._dev(p_pa), latr=self._dev(latr), gp=self._dev(gp), gl=self._dev(gl),
-                 coslat=self._dev(coslat), f=self._dev(f))
+        # the small coordinate / stencil-coefficient vectors are uploaded once per (p, f, coslat) and cached
+        key = (np.asarray(p_pa, dtype=np.float64).tobytes(), np.asarray(f, dtype=np.float64).tobytes(),
+               np.asarray(coslat, dtype=np.float64).tobytes())
+        cached = getattr(self, '_epi_cache', None)
+        if cached is None or cached[0] != key:
+            latr = np.deg2rad(self.lat_out)
+            gp, p_uni, hp = gradient_coefficients(p_pa)
+            gl, l_uni, hl = gradient_coefficients(latr)
+            packed = self._dev(np.concatenate([np.ravel(x) for x in (p_pa, latr, gp, gl, coslat, f)]))
+            nl, nm = len(p_pa), self.M
+            offs = np.cumsum([0, nl, nm, 3 * nl, 3 * nm, nm, nm])
+            d = {n: packed[offs[i]:offs[i + 1]] for i, n in enumerate(('p', 'latr', 'gp', 'gl', 'coslat', 'f'))}
+            d['_packed'] = packed
+            self._epi_cache = (key, d, p_uni, hp, l_uni, hl)
+        _, d, p_uni, hp, l_uni, hl = self._epi_cache
         nout = len(_lib.EPILOGUE_OUTPUTS)
         out = torch.empty((nout + 2, nt, nlev, self.Mld), dtype=torch.float64, device=self.device)
         args = _lib.EpilogueArgs(nt=nt, nlev=nlev, nlat=self.M, ld=self.Mld, zm=zm.data_ptr(), p=d['p'].data_ptr(),

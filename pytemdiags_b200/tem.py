@@ -344,6 +344,9 @@ class TEMDiagnostics:
         eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
         if ntr:
             eng.check_finite(coefq, 'q')
+        self._coef_in = coef           # coefficient rows in the INPUT's level order (for the native-grid properties)
+        self._coefq_in = coefq
+        self._lev_scale = lev_scale
         if self._flip_lev:
             coef = coef.reshape(7, T, K, eng.lpad).flip(2).reshape(7, T * K, eng.lpad).contiguous()
             if ntr:
@@ -446,6 +449,83 @@ class TEMDiagnostics:
     int_vbdp = property(lambda self: self._result('int_vbdp'))
     psi = property(lambda self: self._result('psi'))
     dpsi_dp = property(lambda self: self._result('dpsi_dp'))
+
+    # ---- native-grid eddies and products (tem_diagnostics.py:420-433, 517-529, 547-555): NOT kept by the fused
+    #      path; rebuilt on demand, one field at a time, shaped (ncol, plev, time) like the reference's.
+    def _native(self, which):
+        key = ('native', which)
+        if key in self._cache:
+            return self._cache[key]
+        eng = self.ZM._engine
+        dev = eng.device
+        K, T, N = self.NLEV, self.NT, self.NCOL
+        src = {'up': ('ua', 0, False), 'vp': ('va', 1, False), 'thetap': ('ta', 2, True), 'wapp': ('wap', 3, False)}
+        for i in range(self.ntrac):
+            src['qp%d' % i] = ('q%d' % i, None, False)
+        prod = {'upvp': ('up', 'vp'), 'upwapp': ('up', 'wapp'), 'vptp': ('vp', 'thetap')}
+        for i in range(self.ntrac):
+            prod['qpvp%d' % i] = ('qp%d' % i, 'vp')
+            prod['qpwapp%d' % i] = ('qp%d' % i, 'wapp')
+
+        def eddy(name):
+            var, ci, scaled = src[name]
+            x = self._slab(var, 0, T, dev)
+            c = self._coef_in[ci] if ci is not None else self._coefq_in[3 * int(name[2:])]
+            return eng.eddy_native(x, c, self._lev_scale if scaled else None, K)
+        if which in src:
+            t = eddy(which)
+            like = self._vars[src[which][0]]
+        else:
+            a_, b_ = prod[which]
+            t = eng.multiply(eddy(a_), eddy(b_))
+            like = self._vars[src[a_][0]]
+        t = t.reshape(T, K, N)
+        if self._flip_lev:
+            t = t.flip(1)
+        t = t.permute(2, 1, 0).contiguous()                   # (ncol, plev, time)
+        r = ar.raw(like)
+        in_dev = r.device if isinstance(r, torch.Tensor) else None
+        out = ar.from_device(t, 'numpy' if self._kind == 'dataarray' else self._kind, ar.dtype_of(like), in_dev)
+        if self._kind == 'dataarray':
+            coords = {self.plevname: self.plev, self.timename: self.time}
+            out = ar.make_dataarray(self.ua, out, self.data_dims, coords=coords, name=which.rstrip('0123456789'))
+        self._cache[key] = out
+        return out
+
+    up = property(lambda self: self._native('up'))
+    vp = property(lambda self: self._native('vp'))
+    thetap = property(lambda self: self._native('thetap'))
+    wapp = property(lambda self: self._native('wapp'))
+    upvp = property(lambda self: self._native('upvp'))
+    upwapp = property(lambda self: self._native('upwapp'))
+    vptp = property(lambda self: self._native('vptp'))
+    qp = property(lambda self: [self._native('qp%d' % i) for i in range(self.ntrac)])
+    qpvp = property(lambda self: [self._native('qpvp%d' % i) for i in range(self.ntrac)])
+    qpwapp = property(lambda self: [self._native('qpwapp%d' % i) for i in range(self.ntrac)])
+
+    @property
+    def theta(self):
+        """potential temperature on the native grid (tem_diagnostics.py:491-506), rebuilt on demand on the GPU
+        (theta = lev_scale * T is the eddy kernel with zero coefficients)."""
+        key = ('native', 'theta')
+        if key not in self._cache:
+            eng = self.ZM._engine
+            K, T, N = self.NLEV, self.NT, self.NCOL
+            x = self._slab('ta', 0, T, eng.device)
+            zero = torch.zeros((T * K, eng.lpad), dtype=torch.float64, device=eng.device)
+            t = eng.eddy_native(x, zero, self._lev_scale, K).reshape(T, K, N)
+            if self._flip_lev:
+                t = t.flip(1)
+            t = t.permute(2, 1, 0).contiguous()
+            r = ar.raw(self.ta)
+            in_dev = r.device if isinstance(r, torch.Tensor) else None
+            out = ar.from_device(t, 'numpy' if self._kind == 'dataarray' else self._kind, ar.dtype_of(self.ta), in_dev)
+            if self._kind == 'dataarray':
+                coords = {self.plevname: self.plev, self.timename: self.time}
+                out = ar.make_dataarray(self.ua, out, self.data_dims, coords=coords, name='THETA',
+                                        attrs={'long_name': 'potential temperature'})
+            self._cache[key] = out
+        return self._cache[key]
 
     @property
     def out_file(self):

@@ -163,3 +163,19 @@ def test_zonal_averager_weights_path():
     assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < TOL
     assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < TOL
     assert nerr(ZM.Y0inv, Y0inv) < 1e-13 and nerr(ZM.Y0, Y0) < 1e-12
+
+
+def test_native_grid_properties_on_demand():
+    """up, vp, thetap, wapp, upvp, upwapp, vptp (tem_diagnostics.py:420-433) are rebuilt on request."""
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, plev, f = _case(6, 7, 3, seed=8)
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0)[:, ::-1, :])       # (ncol, plev, time), plev descending
+    tem = TEMDiagnostics(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), lat, p=plev[::-1].copy(), L=25, debug_level=0)
+    ref = _ref(f, plev, lat, 25)
+    for n in ('up', 'vp', 'thetap', 'wapp'):
+        got = getattr(tem, n)
+        assert got.shape == ref[n].shape and nerr(got, ref[n]) < TOL, n
+    assert nerr(tem.upvp, ref['up'] * ref['vp']) < TOL
+    assert nerr(tem.upwapp, ref['up'] * ref['wapp']) < TOL
+    assert nerr(tem.vptp, ref['vp'] * ref['thetap']) < TOL
+    assert nerr(tem.theta, ref['theta']) < 1e-14
