@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -392,6 +393,13 @@ extern "C" int temd_synth_native(temd_plan* p, const double* coef, int rows, dou
     if (p == nullptr || !p->built) return temd_set_error(-1, "synth_native: basis not built");
     if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->N) return temd_set_error(-1, "synth_native: bad arguments");
     TEMD_CUDA(cudaSetDevice(p->dev));
+    static const bool use_res = [] { const char* e = getenv("TEMD_SYNTH_RESIDENT"); return !(e && atoi(e) == 0); }();
+    if (use_res) {
+        const int rc = launch_synth_resident(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, p->sms,
+                                             reinterpret_cast<cudaStream_t>(stream));
+        if (rc == 1) return 0;
+        if (rc != 0) return rc;
+    }
     return launch_synth(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, reinterpret_cast<cudaStream_t>(stream));
 }
 

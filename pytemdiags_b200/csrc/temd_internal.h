@@ -31,6 +31,9 @@ int launch_project(const double* const* x, int nfields, int rows, int ncol, size
 int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b, double* out,
                  size_t ld_out, cudaStream_t stream);
 
+int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b,
+                          double* out, size_t ld_out, int sms, cudaStream_t stream);
+
 // ---- K1 basis + K3 Cholesky/inverse (temd_basis.cu) ----
 int launch_basis(const double* x, int n, int L, const double* rec_a, const double* rec_b, double* qt, size_t ld,
                  int lpad, cudaStream_t stream);
