@@ -75,7 +75,7 @@ __device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st,
     }
 }
 
-template <int BM, int NJ, int WARPS>
+template <int BM, int NJ, int WARPS, bool TWO>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1)
 k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     constexpr int MT = BM / 8;          // m8-tiles per CTA
@@ -260,8 +260,10 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
         }
     };
 
+    // TWO is a template parameter on purpose: with both loop shapes behind a run-time flag ptxas schedules
+    // both of them worse (measured on the sibling kernel k_synth_res: 82 % -> 76 % of peak)
     int i = 0;
-    if (p.nch == 2) {
+    if constexpr (TWO) {
         for (; i + 2 <= nloc; i += 2) round(std::integral_constant<int, 2>{}, i);
     }
     for (; i < nloc; i++) round(std::integral_constant<int, 1>{}, i);
@@ -301,13 +303,19 @@ int eddy_pick_split(int rows, int lpad, int nchunks, int sms) {
 
 size_t eddy_workspace_doubles(int rows, int lpad, int nsplit) { return (size_t)nsplit * 3 * rows * lpad; }
 
-template <int BM, int NJ, int WARPS>
-static int launch_eddy_t(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <int BM, int NJ, int WARPS, bool TWO>
+static int launch_eddy_2(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ, WARPS, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (p.rows + BM - 1) / BM;
-    k_eddy<BM, NJ, WARPS><<<ntiles * p.nsplit, (WARPS + 1) * 32, smem, stream>>>(maps, p);
+    k_eddy<BM, NJ, WARPS, TWO><<<ntiles * p.nsplit, (WARPS + 1) * 32, smem, stream>>>(maps, p);
     return (int)cudaGetLastError();
+}
+
+template <int BM, int NJ, int WARPS>
+static int launch_eddy_t(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
+    return p.nch == 2 ? launch_eddy_2<BM, NJ, WARPS, true>(maps, p, smem, stream)
+                      : launch_eddy_2<BM, NJ, WARPS, false>(maps, p, smem, stream);
 }
 
 int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t ld_x, const double* qt, int lpad,

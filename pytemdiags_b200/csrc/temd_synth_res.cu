@@ -32,7 +32,7 @@ static inline int sr_ls(int lpad) {
     return ls;
 }
 
-template <int MTW>   // m8-tiles per warp: 2 -> BM = 128, 1 -> BM = 64
+template <int MTW, bool TWO>   // MTW: m8-tiles per warp (2 -> BM = 128, 1 -> BM = 64); TWO: two chunks per iteration
 __global__ void __launch_bounds__(SR_THREADS, 1)
 k_synth_res(const __grid_constant__ CUtensorMap qmap, const SynthResParams p) {
     constexpr int BM = SR_WARPS * 8 * MTW;
@@ -148,8 +148,9 @@ k_synth_res(const __grid_constant__ CUtensorMap qmap, const SynthResParams p) {
         }
     };
     int i = 0;
-    if (p.nt > 4)   // two chunks per iteration pay off once the contraction is long enough (measured: L = 25 prefers one)
+    if constexpr (TWO) {
         for (; i + 2 <= nloc; i += 2) round(std::integral_constant<int, 2>{}, i);
+    }
     for (; i < nloc; i++) round(std::integral_constant<int, 1>{}, i);
 }
 
@@ -181,16 +182,18 @@ int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, cons
     CUtensorMap qmap;
     int rc = make_tma_2d(&qmap, b, (uint64_t)ncol, (uint64_t)lpad, ld_b * sizeof(double), TILE_K, p.qbox);
     if (rc) return rc;
-    cudaError_t e;
-    if (mtw == 2) {
-        e = cudaFuncSetAttribute(k_synth_res<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return temd_set_error((int)e, "synth_resident: cudaFuncSetAttribute failed");
-        k_synth_res<2><<<ntiles * p.nsplit, SR_THREADS, smem, stream>>>(qmap, p);
-    } else {
-        e = cudaFuncSetAttribute(k_synth_res<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return temd_set_error((int)e, "synth_resident: cudaFuncSetAttribute failed");
-        k_synth_res<1><<<ntiles * p.nsplit, SR_THREADS, smem, stream>>>(qmap, p);
-    }
+    cudaError_t e = cudaSuccess;
+    // two chunks per iteration pay off once the contraction is long enough (measured: L = 25 prefers one)
+#define SR_LAUNCH(M_, T_)                                                                                         \
+    do {                                                                                                          \
+        e = cudaFuncSetAttribute(k_synth_res<M_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+        if (e != cudaSuccess) return temd_set_error((int)e, "synth_resident: cudaFuncSetAttribute failed");       \
+        k_synth_res<M_, T_><<<ntiles * p.nsplit, SR_THREADS, smem, stream>>>(qmap, p);                             \
+    } while (0)
+    if (mtw == 2 && nt > 4) SR_LAUNCH(2, true);
+    else if (mtw == 2) SR_LAUNCH(2, false);
+    else SR_LAUNCH(1, true);
+#undef SR_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess) return temd_set_error((int)e, "synth_resident: kernel launch failed");
     return 1;

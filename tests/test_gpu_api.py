@@ -179,3 +179,28 @@ def test_native_grid_properties_on_demand():
     assert nerr(tem.upwapp, ref['up'] * ref['wapp']) < TOL
     assert nerr(tem.vptp, ref['vp'] * ref['thetap']) < TOL
     assert nerr(tem.theta, ref['theta']) < 1e-14
+
+
+def test_odd_column_count_and_pole_points():
+    """N odd (the TMA path needs an even leading dimension: the host pads) and zm_pole_points=True
+    (M = 181 odd; 1/(a cos(lat)) is ~1e9 at the poles, same arithmetic as the reference, tem_diagnostics.py:391-394)."""
+    from pytemdiags_b200 import TEMDiagnostics, sph_zonal_averager
+    lat, lon = syn.latlon_grid(15, 7, poles=False)
+    assert lat.shape[0] % 2 == 1
+    K, T, L = 6, 2, 8
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=9)
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=L, dims=('time', 'lev', 'ncol'),
+                         debug_level=0, zm_pole_points=True)
+    ref = _ref(f, plev, lat, L, zm_pole_points=True)
+    assert tem.ZM_N == 181
+    for n in ALL:
+        got = getattr(tem, n)
+        got = got() if callable(got) else got
+        assert got.shape == ref[n].shape and nerr(got, ref[n]) < TOL, (n, nerr(got, ref[n]))
+    ZM = sph_zonal_averager(lat, np.arange(-89.5, 90, 1.0), L)
+    ZM.sph_compute_matrices()
+    A = np.random.default_rng(3).standard_normal((lat.shape[0], 5))
+    Y0, Y0inv, Y0p = oracle.sph_matrices(lat, np.arange(-89.5, 90, 1.0), L)
+    assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < TOL
+    assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < TOL
