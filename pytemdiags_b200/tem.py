@@ -308,6 +308,9 @@ class TEMDiagnostics:
         budget = budget * 4 // (4 + ntr)
         ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
         names = ('ua', 'va', 'ta', 'wap') + tuple('q{}'.format(i) for i in range(ntr))
+        fused = eng.lpad <= 408
+        if not fused:
+            ts = max(1, ts // 3)      # the staged path keeps 3 eddies + 3 products of a slab resident
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
@@ -329,17 +332,37 @@ class TEMDiagnostics:
                 for x in xs:
                     x.record_stream(main)
                 c4 = eng.project(xs[:4], lev_scale=lev_scale, scale_field=2, nlev=K)
-                cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
                 coef[:4, t0 * K:t1 * K] = c4
-                coef[4:, t0 * K:t1 * K] = cf
-                for i in range(ntr):
-                    # tracer i (tem_diagnostics.py:532-538, 560-570): the fused kernel on (q, v, theta, omega)
-                    # returns q'v' and q'omega' in its first two product slots
-                    cq = eng.project([xs[4 + i]])
-                    c4q = torch.cat([cq, c4[1:]], 0)
-                    cfq = eng.eddy_flux_project(xs[4 + i], xs[1], xs[2], xs[3], c4q, lev_scale, K)
-                    coefq[3 * i, t0 * K:t1 * K] = cq[0]
-                    coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = cfq[:2]
+                if fused:
+                    cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
+                    coef[4:, t0 * K:t1 * K] = cf
+                    for i in range(ntr):
+                        # tracer i (tem_diagnostics.py:532-538, 560-570): the fused kernel on (q, v, theta, omega)
+                        # returns q'v' and q'omega' in its first two product slots
+                        cq = eng.project([xs[4 + i]])
+                        c4q = torch.cat([cq, c4[1:]], 0)
+                        cfq = eng.eddy_flux_project(xs[4 + i], xs[1], xs[2], xs[3], c4q, lev_scale, K)
+                        coefq[3 * i, t0 * K:t1 * K] = cq[0]
+                        coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = cfq[:2]
+                else:
+                    # L + 1 > 408: the coefficient tile of the fused kernel no longer fits in shared memory.
+                    # Staged GPU path: native means -> eddies -> products -> projections (eddies ARE materialised).
+                    eu = eng.eddy_native(xs[0], c4[0])
+                    ev = eng.eddy_native(xs[1], c4[1])
+                    ew = eng.eddy_native(xs[3], c4[3])
+                    prods = [eng.multiply(eu, ev), eng.multiply(eu, ew)]
+                    et = eng.eddy_native(xs[2], c4[2], lev_scale, K)
+                    prods.append(eng.multiply(ev, et))
+                    del et, eu
+                    coef[4:, t0 * K:t1 * K] = eng.project(prods)
+                    del prods
+                    for i in range(ntr):
+                        cq = eng.project([xs[4 + i]])
+                        eq = eng.eddy_native(xs[4 + i], cq[0])
+                        coefq[3 * i, t0 * K:t1 * K] = cq[0]
+                        coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = eng.project([eng.multiply(eq, ev), eng.multiply(eq, ew)])
+                        del eq
+                    del ev, ew
                 del xs
         eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
         if ntr:

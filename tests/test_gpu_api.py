@@ -204,3 +204,21 @@ def test_odd_column_count_and_pole_points():
     Y0, Y0inv, Y0p = oracle.sph_matrices(lat, np.arange(-89.5, 90, 1.0), L)
     assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < TOL
     assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < TOL
+
+
+def test_large_L_staged_path():
+    """L + 1 > 408 exceeds the fused kernel's shared-memory budget: the staged GPU path must give the same answers."""
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon = syn.pg2_grid(72)            # 124,416 columns: cond(Y0) = 6 at L = 420
+    K, T, L = 5, 1, 420
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=10)
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=L, dims=('time', 'lev', 'ncol'), debug_level=0)
+    assert tem.ZM._engine.lpad > 408
+    mats = oracle.sph_matrices(lat, oracle.zm_latitudes(1), L, method='normal', basis='recurrence')
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0))
+    ref = oracle.tem_suite(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), plev, lat, L=L, literal=False, matrices=mats)
+    for n in ALL:
+        got = getattr(tem, n)
+        got = got() if callable(got) else got
+        assert nerr(got, ref[n]) < TOL, (n, nerr(got, ref[n]))
