@@ -168,7 +168,17 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = None
     if world > 1:
+        # bind this rank to the CPUs / NUMA node next to its GPU so that pinned host buffers are local to the
+        # GPU's PCIe root (8 ranks copying at once otherwise share one socket's memory bandwidth)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = 'nvml cpu affinity (%d cpus)' % len(os.sched_getaffinity(0))
+        except Exception as e:      # noqa: BLE001
+            numa = 'unbound (%s)' % type(e).__name__
         dist.init_process_group('nccl', device_id=dev)
 
     cfg, L = workload(args.config)
@@ -298,7 +308,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {'value': N * K * Te * world / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-               'time_steps_per_call': Te, 'ms_per_call': dt * 1e3, 'pinned_h2d_gbs_measured': h2d_gbs,
+               'time_steps_per_call': Te, 'ms_per_call': dt * 1e3, 'pinned_h2d_gbs_measured': h2d_gbs, 'cpu_binding': numa,
                'note': 'public API TEMDiagnostics(ua, va, ta, wap, p, lat) on pinned host arrays; H2D of slab i+1 overlaps '
                        'compute of slab i; basis cached across calls like the reference\'s maps/ cache'}
 

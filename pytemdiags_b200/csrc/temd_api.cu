@@ -99,19 +99,19 @@ __global__ void k_trace_offdiag(const double* __restrict__ G, int n, int ld, dou
 __global__ void k_eddy_native(const double* __restrict__ x, size_t ld_x, const double* __restrict__ scale, int nlev,
                               double* __restrict__ out, size_t ld_out, int rows, int n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (i >= (size_t)n || r >= rows) return;
-    const double s = scale ? scale[r % nlev] : 1.0;
-    out[(size_t)r * ld_out + i] = s * x[(size_t)r * ld_x + i] - out[(size_t)r * ld_out + i];
+    if (i >= (size_t)n) return;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        const double s = scale ? scale[r % nlev] : 1.0;
+        out[(size_t)r * ld_out + i] = s * x[(size_t)r * ld_x + i] - out[(size_t)r * ld_out + i];
+    }
 }
 
 // out = a .* b
 __global__ void k_mul(const double* __restrict__ a, size_t ld_a, const double* __restrict__ b, size_t ld_b,
                       double* __restrict__ out, size_t ld_out, int rows, int n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (i >= (size_t)n || r >= rows) return;
-    out[(size_t)r * ld_out + i] = a[(size_t)r * ld_a + i] * b[(size_t)r * ld_b + i];
+    if (i >= (size_t)n) return;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) out[(size_t)r * ld_out + i] = a[(size_t)r * ld_a + i] * b[(size_t)r * ld_b + i];
 }
 
 // out[l][n] = in[l][n] * w[n]   (Y0inv = Y0^T diag(w), reference sph_zonal_mean.py:383-386)
@@ -464,7 +464,7 @@ extern "C" int temd_eddy_native(temd_plan* p, const double* x, size_t ld_x, cons
     TEMD_CUDA(cudaSetDevice(p->dev));
     int rc = launch_synth(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, st);
     if (rc) return rc;
-    dim3 grid((p->N + 255) / 256, rows);
+    dim3 grid((p->N + 255) / 256, rows < 32768 ? rows : 32768);
     k_eddy_native<<<grid, 256, 0, st>>>(x, ld_x, lev_scale, nlev < 1 ? 1 : nlev, out, ld_out, rows, p->N);
     TEMD_CUDA(cudaGetLastError());
     return 0;
@@ -473,7 +473,7 @@ extern "C" int temd_eddy_native(temd_plan* p, const double* x, size_t ld_x, cons
 extern "C" int temd_multiply(const double* a, size_t ld_a, const double* b, size_t ld_b, double* out, size_t ld_out,
                              int rows, int ncol, void* stream) {
     if (!a || !b || !out || rows < 1 || ncol < 1) return temd_set_error(-1, "multiply: bad arguments");
-    dim3 grid((ncol + 255) / 256, rows);
+    dim3 grid((ncol + 255) / 256, rows < 32768 ? rows : 32768);
     k_mul<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, ld_a, b, ld_b, out, ld_out, rows, ncol);
     TEMD_CUDA(cudaGetLastError());
     return 0;
