@@ -81,8 +81,10 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     constexpr int MT = BM / 8;          // m8-tiles per CTA
     constexpr int NW2 = WARPS / MT;     // warps per m-tile group (2, 4, 8 or 16)
     // GEMM1: a group owns 8 units (4 fields x 2 n8-tiles of the 16-column chunk) of its m-tile
-    constexpr int NF1 = (NW2 == 2) ? 2 : 1;   // fields per warp
-    constexpr int NN1 = (NW2 >= 8) ? 1 : 2;   // n8-tiles per warp
+    //   NW2 = 2: 2 fields x 2 n-tiles per warp;  NW2 = 4: 2 fields x 1 n-tile (fewest LDS per DMMA once two chunks
+    //   share the coefficient fragments);  NW2 = 8: 1 field x 1 n-tile
+    constexpr int NF1 = (NW2 <= 4) ? 2 : 1;   // fields per warp
+    constexpr int NN1 = (NW2 == 2) ? 2 : 1;   // n8-tiles per warp
     constexpr int XF_BYTES = BM * TILE_ROW_BYTES;   // one field's X tile
     static_assert(NW2 == 2 || NW2 == 4 || NW2 == 8, "unsupported warp layout");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -152,8 +154,8 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     // CTA.  Groups are laid out so that the warps sharing an SM sub-partition (warp % 4) belong to
     // different groups and carry complementary GEMM2 loads.
     const int mi = warp / NW2, r_in = warp % NW2;
-    const int f1 = (NW2 == 2) ? r_in * 2 : (NW2 == 4 ? r_in : (r_in >> 1) & 3);
-    const int jn1 = (NW2 >= 8) ? (r_in & 1) : 0;
+    const int f1 = (NW2 == 2) ? r_in * 2 : (NW2 == 4 ? (r_in & 1) * 2 : (r_in >> 1) & 3);
+    const int jn1 = (NW2 == 2) ? 0 : (NW2 == 4 ? (r_in >> 1) : (r_in & 1));
     const int wq = (r_in + ((NW2 == 2) ? (mi >> 1) : mi)) % NW2;
     const int grp_bar = 1 + mi, grp_threads = NW2 * 32;
     const int j_begin = (wq * p.nt) / NW2;
