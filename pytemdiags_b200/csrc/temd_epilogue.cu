@@ -81,22 +81,61 @@ __global__ void k_epi_a(const EpiDev e) {
     OUT(TEMD_OUT_PSICOSLAT)[idx] = psi * c0;                                          // :592
 }
 
-// int_vbdp (tem_util.py:230-232): cumulative trapezoid from the model top, one thread per (t, lat)
-__global__ void k_epi_scan(const EpiDev e) {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)e.nt * e.nlat) return;
-    const int m = (int)(gid % e.nlat), t = (int)(gid / e.nlat);
-    const double* vb = ZM(Z_VB);
-    double* o = OUT(TEMD_OUT_INT_VBDP);
-    size_t idx = (size_t)t * e.nlev * e.ld + m;
-    double acc = 0.0, prev = vb[idx];
-    o[idx] = 0.0;
-    for (int k = 1; k < e.nlev; k++) {
-        idx += e.ld;
-        const double cur = vb[idx];
-        acc += (e.p[k] - e.p[k - 1]) * (cur + prev) / 2.0;
-        o[idx] = acc;
-        prev = cur;
+// int_vbdp (tem_util.py:230-232): cumulative trapezoid from the model top,
+//   out[k] = sum_{j<=k} (p_j - p_{j-1}) (v_j + v_{j-1}) / 2,  out[0] = 0.
+// One CTA per (time step, 32 latitudes): the [nlev][32] slab is staged through shared memory with coalesced
+// loads, each warp scans 4 latitude columns along the level axis with warp shuffles (32 levels per pass, running
+// carry between passes), and the result leaves through shared memory again so the stores are coalesced too.
+constexpr int SCAN_LATS = 32;
+constexpr int SCAN_MAXLEV = 160;     // levels staged per pass (shared memory: 2 x 160 x 32 x 8 B = 80 KB dynamic)
+
+__global__ void __launch_bounds__(256) k_epi_scan(const EpiDev e) {
+    extern __shared__ double sm[];
+    double* sv = sm;                                   // [lev][32]
+    double* so = sm + (size_t)SCAN_MAXLEV * SCAN_LATS; // [lev][32]
+    const int t = blockIdx.y;
+    const int lat0 = blockIdx.x * SCAN_LATS;
+    const int nl = min(SCAN_LATS, e.nlat - lat0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* vb = ZM(Z_VB) + (size_t)t * e.nlev * e.ld + lat0;
+    double* o = OUT(TEMD_OUT_INT_VBDP) + (size_t)t * e.nlev * e.ld + lat0;
+    double carry[4] = {0.0, 0.0, 0.0, 0.0};            // running integral of this warp's 4 columns
+    double vprev[4] = {0.0, 0.0, 0.0, 0.0};            // v at the last level of the previous pass
+    for (int k0 = 0; k0 < e.nlev; k0 += SCAN_MAXLEV) {
+        const int nk = min(SCAN_MAXLEV, e.nlev - k0);
+        for (int i = threadIdx.x; i < nk * SCAN_LATS; i += blockDim.x) {
+            const int k = i / SCAN_LATS, m = i % SCAN_LATS;
+            sv[i] = (m < nl) ? vb[(size_t)(k0 + k) * e.ld + m] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int m = warp * 4 + c;
+            for (int kb = 0; kb < nk; kb += 32) {
+                const int k = kb + lane, kg = k0 + k;
+                double term = 0.0;
+                if (k < nk && kg > 0) {
+                    const double v1 = sv[k * SCAN_LATS + m];
+                    const double v0 = (k > 0) ? sv[(k - 1) * SCAN_LATS + m] : vprev[c];
+                    term = (e.p[kg] - e.p[kg - 1]) * (v1 + v0) / 2.0;
+                }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {      // inclusive warp scan
+                    const double up = __shfl_up_sync(0xffffffffu, term, d);
+                    if (lane >= d) term += up;
+                }
+                term += carry[c];
+                if (k < nk) so[k * SCAN_LATS + m] = term;
+                carry[c] = __shfl_sync(0xffffffffu, term, 31);
+            }
+            vprev[c] = sv[(nk - 1) * SCAN_LATS + m];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nk * SCAN_LATS; i += blockDim.x) {
+            const int k = i / SCAN_LATS, m = i % SCAN_LATS;
+            if (m < nl) o[(size_t)(k0 + k) * e.ld + m] = so[i];
+        }
+        __syncthreads();
     }
 }
 
@@ -244,7 +283,13 @@ int launch_tem_epilogue(const EpilogueArgs& wrap, cudaStream_t stream) {
     const size_t total = (size_t)a.nt * a.nlev * a.nlat;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     k_epi_a<<<blocks, 256, 0, stream>>>(e);
-    k_epi_scan<<<(unsigned)(((size_t)a.nt * a.nlat + 127) / 128), 128, 0, stream>>>(e);
+    {
+        const int smem = 2 * SCAN_MAXLEV * SCAN_LATS * (int)sizeof(double);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_epi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        dim3 grid((a.nlat + SCAN_LATS - 1) / SCAN_LATS, a.nt);
+        k_epi_scan<<<grid, 256, smem, stream>>>(e);
+    }
     k_epi_b<<<blocks, 256, 0, stream>>>(e);
     k_epi_c<<<blocks, 256, 0, stream>>>(e);
     return (int)cudaGetLastError();
