@@ -285,8 +285,7 @@ int launch_tem_epilogue(const EpilogueArgs& wrap, cudaStream_t stream) {
     k_epi_a<<<blocks, 256, 0, stream>>>(e);
     {
         const int smem = 2 * SCAN_MAXLEV * SCAN_LATS * (int)sizeof(double);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_epi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        cudaFuncSetAttribute(k_epi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device
         dim3 grid((a.nlat + SCAN_LATS - 1) / SCAN_LATS, a.nt);
         k_epi_scan<<<grid, 256, smem, stream>>>(e);
     }

@@ -126,12 +126,9 @@ int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double*
     if (rc) return rc;
     if ((ld_out & 1) || (reinterpret_cast<uintptr_t>(out) & 15)) return temd_set_error(-1, "synth: output must be 16-byte aligned with an even leading dimension");
     constexpr int smem = SY_STAGES * SY_STAGE_BYTES + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return temd_set_error((int)e, "synth: cudaFuncSetAttribute failed");
-        attr_set = true;
-    }
+    // per-device attribute: set on every launch (cheap) so that several devices in one process all work
+    cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return temd_set_error((int)e, "synth: cudaFuncSetAttribute failed");
     dim3 grid((rows + SY_BM - 1) / SY_BM, (ncol + SY_BN - 1) / SY_BN);
     const int nkb = (lpad + SY_BK - 1) / SY_BK;
     k_synth<<<grid, SY_THREADS, smem, stream>>>(maps, rows, ncol, nkb, out, ld_out);

@@ -286,6 +286,42 @@ class TEMDiagnostics:
             x = buf[:, :N]
         return x
 
+    def _is_native_device_layout(self, var, device):
+        '''True if the input is a float64 CUDA tensor on `device`, C-contiguous in (time, lev, ncol) order with an even,
+        16-byte aligned row pitch: the kernels can then read it in place.'''
+        r = ar.raw(self._vars[var])
+        dims = self._in_dims[var]
+        return (isinstance(r, torch.Tensor) and r.is_cuda and r.device == device and r.dtype == torch.float64
+                and dims == (self.timename, self.plevname, self.ncolname) and r.is_contiguous()
+                and self.NCOL % 2 == 0 and r.data_ptr() % 16 == 0)
+
+    def _fill(self, dst, var, t0, t1, device):
+        '''Copy time steps [t0, t1) of one input into the staging buffer dst [(t1-t0)*K][ld] (float64, (time, lev,
+        ncol) order).  Host arrays in that order go straight into place with one asynchronous copy (a true DMA when
+        pinned); other layouts / dtypes / devices are uploaded as they are and permuted on the device.'''
+        r = ar.raw(self._vars[var])
+        dims = self._in_dims[var]
+        if self.timename in dims:
+            sl = [slice(None)] * r.ndim
+            sl[dims.index(self.timename)] = slice(t0, t1)
+            r = r[tuple(sl)]
+        else:
+            r = r[..., None] if isinstance(r, np.ndarray) else r.unsqueeze(-1)
+            dims = dims + (self.timename,)
+        perm = [dims.index(self.timename), dims.index(self.plevname), dims.index(self.ncolname)]
+        K, N = self.NLEV, self.NCOL
+        view = dst[:(t1 - t0) * K].view(t1 - t0, K, dst.shape[1])[:, :, :N]
+        if isinstance(r, np.ndarray):
+            if r.dtype.byteorder not in ('=', '|') or not r.flags.writeable:
+                r = np.array(r, dtype=r.dtype.newbyteorder('='))
+            if not (r.flags.c_contiguous or r.flags.f_contiguous):
+                r = np.ascontiguousarray(r)     # strided host slice (time is not the leading dim): pack on the host
+            r = torch.from_numpy(r)
+        if perm == [0, 1, 2] and not r.is_cuda and r.is_contiguous():
+            view.copy_(r, non_blocking=True)
+        else:
+            view.copy_(r.to(device, non_blocking=True).permute(*perm))
+
     def _compute_all(self):
         '''_compute_potential_temperature, _decompose_zm_eddy, _compute_fluxes, _compute_derivatives
         (tem_diagnostics.py:491-611) and every diagnostics method (:615-797), on the GPU.
@@ -299,71 +335,96 @@ class TEMDiagnostics:
         # theta = T (p0/p)^k per level (tem_diagnostics.py:498), in the input's level order
         p_in = self._plev_input_order * 100
         lev_scale = eng._dev((self.p0 / p_in) ** const.k)
-        on_host = not isinstance(ar.raw(self.ua), torch.Tensor) or not ar.raw(self.ua).is_cuda
-        budget = self._slab_bytes if self._slab_bytes is not None else ((2 << 30) if on_host else (16 << 30))
-        ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
-        coef = torch.empty((7, T * K, eng.lpad), dtype=torch.float64, device=dev)
         ntr = self.ntrac
-        coefq = torch.empty((3 * ntr, T * K, eng.lpad), dtype=torch.float64, device=dev) if ntr else None
-        budget = budget * 4 // (4 + ntr)
-        ts = max(1, min(T, int(budget // (4 * 8 * K * N))))
         names = ('ua', 'va', 'ta', 'wap') + tuple('q{}'.format(i) for i in range(ntr))
+        nf = len(names)
+        ld = N + (N & 1)
+        zero_copy = all(self._is_native_device_layout(v, dev) for v in names)
+        budget = self._slab_bytes if self._slab_bytes is not None else ((16 << 30) if zero_copy else (2 << 30))
         fused = eng.lpad <= 408
+        ts = max(1, min(T, int(budget // (nf * 8 * K * N))))
         if not fused:
             ts = max(1, ts // 3)      # the staged path keeps 3 eddies + 3 products of a slab resident
+        coef = torch.empty((7, T * K, eng.lpad), dtype=torch.float64, device=dev)
+        coefq = torch.empty((3 * ntr, T * K, eng.lpad), dtype=torch.float64, device=dev) if ntr else None
+
+        def compute(xs, t0, t1):
+            c4 = eng.project(xs[:4], lev_scale=lev_scale, scale_field=2, nlev=K)
+            coef[:4, t0 * K:t1 * K] = c4
+            if fused:
+                cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
+                coef[4:, t0 * K:t1 * K] = cf
+                for i in range(ntr):
+                    # tracer i (tem_diagnostics.py:532-538, 560-570): the fused kernel on (q, v, theta, omega)
+                    # returns q'v' and q'omega' in its first two product slots
+                    cq = eng.project([xs[4 + i]])
+                    c4q = torch.cat([cq, c4[1:]], 0)
+                    cfq = eng.eddy_flux_project(xs[4 + i], xs[1], xs[2], xs[3], c4q, lev_scale, K)
+                    coefq[3 * i, t0 * K:t1 * K] = cq[0]
+                    coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = cfq[:2]
+            else:
+                # L + 1 > 408: the coefficient tile of the fused kernel no longer fits in shared memory.
+                # Staged GPU path: native means -> eddies -> products -> projections (eddies ARE materialised).
+                eu = eng.eddy_native(xs[0], c4[0])
+                ev = eng.eddy_native(xs[1], c4[1])
+                ew = eng.eddy_native(xs[3], c4[3])
+                prods = [eng.multiply(eu, ev), eng.multiply(eu, ew)]
+                et = eng.eddy_native(xs[2], c4[2], lev_scale, K)
+                prods.append(eng.multiply(ev, et))
+                del et, eu
+                coef[4:, t0 * K:t1 * K] = eng.project(prods)
+                del prods
+                for i in range(ntr):
+                    cq = eng.project([xs[4 + i]])
+                    eq = eng.eddy_native(xs[4 + i], cq[0])
+                    coefq[3 * i, t0 * K:t1 * K] = cq[0]
+                    coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = eng.project([eng.multiply(eq, ev), eng.multiply(eq, ew)])
+                    del eq
+
         with torch.cuda.device(dev):
-            main = torch.cuda.current_stream(dev)
-            side = torch.cuda.Stream(dev)
-
-            def fetch(t0):
-                t1 = min(T, t0 + ts)
+            if zero_copy:
+                # float64 CUDA tensors already laid out (time, lev, ncol): the kernels read them in place
+                for t0 in range(0, T, ts):
+                    t1 = min(T, t0 + ts)
+                    compute([ar.raw(self._vars[v])[t0:t1].reshape(-1, N) for v in names], t0, t1)
+            else:
+                # two fixed staging sets: slab i+1 is copied / re-laid-out on a side stream into one set while
+                # slab i is computed from the other (no per-slab allocation, no cross-stream allocator traffic)
+                main = torch.cuda.current_stream(dev)
+                side = torch.cuda.Stream(dev)
+                bufs = [[torch.empty((ts * K, ld), dtype=torch.float64, device=dev) for _ in names] for _ in range(2)]
+                if ld != N:
+                    for set_ in bufs:
+                        for b_ in set_:
+                            b_[:, N:].zero_()
+                filled = [None, None]
+                consumed = [None, None]
                 side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    xs = [self._slab(v, t0, t1, dev) for v in names]
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                return xs, ev, t0, t1
 
-            nxt = fetch(0)
-            while nxt is not None:
-                xs, ev, t0, t1 = nxt
-                nxt = fetch(t1) if t1 < T else None
-                main.wait_event(ev)
-                for x in xs:
-                    x.record_stream(main)
-                c4 = eng.project(xs[:4], lev_scale=lev_scale, scale_field=2, nlev=K)
-                coef[:4, t0 * K:t1 * K] = c4
-                if fused:
-                    cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
-                    coef[4:, t0 * K:t1 * K] = cf
-                    for i in range(ntr):
-                        # tracer i (tem_diagnostics.py:532-538, 560-570): the fused kernel on (q, v, theta, omega)
-                        # returns q'v' and q'omega' in its first two product slots
-                        cq = eng.project([xs[4 + i]])
-                        c4q = torch.cat([cq, c4[1:]], 0)
-                        cfq = eng.eddy_flux_project(xs[4 + i], xs[1], xs[2], xs[3], c4q, lev_scale, K)
-                        coefq[3 * i, t0 * K:t1 * K] = cq[0]
-                        coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = cfq[:2]
-                else:
-                    # L + 1 > 408: the coefficient tile of the fused kernel no longer fits in shared memory.
-                    # Staged GPU path: native means -> eddies -> products -> projections (eddies ARE materialised).
-                    eu = eng.eddy_native(xs[0], c4[0])
-                    ev = eng.eddy_native(xs[1], c4[1])
-                    ew = eng.eddy_native(xs[3], c4[3])
-                    prods = [eng.multiply(eu, ev), eng.multiply(eu, ew)]
-                    et = eng.eddy_native(xs[2], c4[2], lev_scale, K)
-                    prods.append(eng.multiply(ev, et))
-                    del et, eu
-                    coef[4:, t0 * K:t1 * K] = eng.project(prods)
-                    del prods
-                    for i in range(ntr):
-                        cq = eng.project([xs[4 + i]])
-                        eq = eng.eddy_native(xs[4 + i], cq[0])
-                        coefq[3 * i, t0 * K:t1 * K] = cq[0]
-                        coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = eng.project([eng.multiply(eq, ev), eng.multiply(eq, ew)])
-                        del eq
-                    del ev, ew
-                del xs
+                def fill(i, t0):
+                    t1 = min(T, t0 + ts)
+                    with torch.cuda.stream(side):
+                        if consumed[i % 2] is not None:
+                            side.wait_event(consumed[i % 2])
+                        for v, dst in zip(names, bufs[i % 2]):
+                            self._fill(dst, v, t0, t1, dev)
+                        ev_ = torch.cuda.Event()
+                        ev_.record(side)
+                    filled[i % 2] = ev_
+                    return t1
+
+                starts = list(range(0, T, ts))
+                fill(0, starts[0])
+                for i, t0 in enumerate(starts):
+                    t1 = min(T, t0 + ts)
+                    if i + 1 < len(starts):
+                        fill(i + 1, starts[i + 1])
+                    main.wait_event(filled[i % 2])
+                    compute([b_[:(t1 - t0) * K, :N] for b_ in bufs[i % 2]], t0, t1)
+                    ev_ = torch.cuda.Event()
+                    ev_.record(main)
+                    consumed[i % 2] = ev_
+                main.wait_stream(side)
         eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
         if ntr:
             eng.check_finite(coefq, 'q')
