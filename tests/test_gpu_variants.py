@@ -1,0 +1,72 @@
+"""GPU: every tile-shape variant of the fused kernels on small problems (compute-sanitizer is closed on the
+pool, so coverage of ragged tiles / empty split ranges / tiny and large L comes from parity alone).
+
+k_eddy picks BM = 32 / 16 / 8 rows for L+1 <= 104 / 208 / 408 and 16 or 8 consumer warps; k_project picks
+1..13 n8-tiles per l-block and 1..4 l-blocks; rows are deliberately not multiples of the row tiles."""
+import numpy as np
+import pytest
+
+import oracle
+from pytemdiags_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+ZM7 = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb')
+
+
+def nerr(x, ref):
+    return float(np.abs(np.asarray(x) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+CASES = [
+    # ne, K, T, L            what it exercises
+    (3, 3, 1, 2),            # L+1 = 3: one n8-tile, most GEMM2 warps idle
+    (3, 2, 2, 7),            # L+1 = 8 exactly
+    (4, 7, 3, 8),            # L+1 = 9 -> 2 tiles, rows = 21
+    (5, 5, 3, 17),           # 3 tiles
+    (6, 9, 5, 33),           # 5 tiles, rows = 45 (two 32-row tiles, second ragged)
+    (8, 11, 3, 62),          # 8 tiles
+    (10, 13, 3, 90),         # 12 tiles
+    (12, 6, 5, 103),         # 13 tiles (largest BM = 32 case), rows = 30
+    (20, 5, 3, 104),         # 14 tiles -> BM = 16
+    (20, 7, 3, 130),         # 17 tiles, rows = 21
+    (32, 3, 3, 207),         # 26 tiles (largest BM = 16 case)
+    (32, 5, 1, 210),         # 27 tiles -> BM = 8, 8 warps
+    (32, 3, 2, 250),         # 32 tiles
+]
+
+
+@pytest.mark.parametrize('ne,K,T,L', CASES)
+def test_fused_path_variants(ne, K, T, L):
+    import torch
+    from pytemdiags_b200.engine import Engine
+    lat, lon = syn.pg2_grid(ne)
+    N = lat.shape[0]
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=100 + L)
+    lat_out = oracle.zm_latitudes(1)
+    mats = oracle.sph_matrices(lat, lat_out, L, method='normal' if N > 6000 else 'auto',
+                               basis='recurrence' if N > 6000 else 'scipy')
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0))
+    ref = oracle.tem_suite(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), plev, lat, L=L, literal=False, matrices=mats)
+    eng = Engine(lat, lat_out, L).build_basis()
+    C = oracle.CONSTANTS
+    sc = torch.as_tensor((C['P0'] / (plev * 100)) ** C['k']).cuda()
+    xs = [torch.as_tensor(f[n].reshape(T * K, N)).cuda() for n in ('ua', 'va', 'ta', 'wap')]
+    c4 = eng.project(xs, lev_scale=sc, scale_field=2, nlev=K)
+    cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, sc, K)
+    zm = eng.synth_out(torch.cat([c4, cf], 0)).cpu().numpy().reshape(7, T, K, -1)
+    for i, n in enumerate(ZM7):
+        e = nerr(zm[i].transpose(2, 1, 0), ref[n])
+        assert e < TOL, (n, e)
+    nat = eng.synth_native(c4[0]).cpu().numpy()
+    Y0, Y0inv, _ = mats
+    assert nerr(nat, (Y0 @ (Y0inv @ f['ua'].reshape(T * K, N).T)).T) < TOL
+
+
+@pytest.mark.parametrize('warps', ['8', '16'])
+def test_eddy_warp_layouts(monkeypatch, warps):
+    """both consumer-warp layouts of k_eddy (the default is 16 for BM >= 16)"""
+    monkeypatch.setenv('TEMD_EDDY_WARPS', warps)
+    test_fused_path_variants(8, 11, 3, 62)
+    test_fused_path_variants(20, 7, 3, 130)
