@@ -15,6 +15,15 @@
 // B operand of both: "MN-major" (contraction over tile rows) in GEMM1, "K-major" in GEMM2.
 // C_f lives in shared memory for the CTA's lifetime (row-major, row stride = 4 or 12 mod 16
 // doubles so that the GEMM1 A fragments are bank-conflict-free under the mnmajor_k permutation).
+//
+// Warp organisation (measured choices): 16 consumer warps + 1 TMA producer warp; the
+// 4 (BM=32) / 8 (BM=16) warps that own one 8-row m-tile form a group that synchronises on its own named
+// barrier for the GEMM1 -> GEMM2 hand-off; one barrier round covers two pipeline stages when four stages fit
+// (GEMM1 of both chunks shares the coefficient fragments).  BM = 32 / 16 / 8 rows for L+1 <= 104 / 208 / 408 is
+// dictated by the 4 x BM x lpad coefficient tile that must stay resident next to >= 2 pipeline stages.
+// Tried and rejected (slower): predicated per-(tile, product) work splitting to balance GEMM2 across a group
+// (27.0 vs 32.6 TFLOP/s: predicated DMMA + WARPSYNC), run-time selection between loop shapes inside one kernel
+// (ptxas schedules both worse; loop shapes are template parameters instead).
 #include <cstdlib>
 #include <type_traits>
 
