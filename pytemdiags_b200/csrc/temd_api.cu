@@ -114,6 +114,11 @@ __global__ void k_mul(const double* __restrict__ a, size_t ld_a, const double* _
     for (int r = blockIdx.y; r < rows; r += gridDim.y) out[(size_t)r * ld_out + i] = a[(size_t)r * ld_a + i] * b[(size_t)r * ld_b + i];
 }
 
+__global__ void k_add_diag(double* __restrict__ G, int ld, int n, double s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) G[(size_t)i * ld + i] += s;
+}
+
 // out[l][n] = in[l][n] * w[n]   (Y0inv = Y0^T diag(w), reference sph_zonal_mean.py:383-386)
 __global__ void k_scale_cols(const double* __restrict__ in, const double* __restrict__ w, double* __restrict__ out,
                              int rows, int n, size_t ld) {
@@ -256,28 +261,49 @@ extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_o
     // K1: raw basis (transposed) on both grids
     if ((rc = launch_basis(p->x, p->N, p->L, p->rec_a, p->rec_b, p->qt_alt, p->ld_q, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
     if ((rc = launch_basis(p->x_out, p->M, p->L, p->rec_a, p->rec_b, p->qpt_alt, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
-    // CholeskyQR pass 1: G = Y0^T Y0 = L1 L1^T,  Q1 = Y0 L1^-T
-    if ((rc = gram_of(p, p->qt_alt, st))) return rc;
-    if ((rc = launch_chol_inv(p->gram, p->lpad, p->Lp, p->lt, p->linv1, p->lpad, p->lpad, p->status, st))) return temd_set_error(rc, "cholesky launch failed");
+    // CholeskyQR2: G = Y^T Y = L L^T, Y <- Y L^-T, twice (the second pass removes the cond(Y0)^2 eps loss of
+    // orthogonality of the first); L^-1 accumulates as L2^-1 L1^-1.  If the first factorisation breaks down
+    // (cond(Y0) >~ 3e6), a shifted first pass (G + s I, s = 11 (N Lp + Lp(Lp+1)) eps trace(G), "shifted
+    // CholeskyQR3") pre-conditions the basis and one more pass is run.  A breakdown after that means Y0 is
+    // numerically rank-deficient (where LAPACK gelsd would truncate): fail loudly.
     int status = 0;
-    TEMD_CUDA(cudaMemcpyAsync(&status, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TEMD_CUDA(cudaStreamSynchronize(st));
-    if (status != 0)
-        return temd_set_error(-5, "basis_build: Y0 is numerically rank-deficient (Cholesky pivot %d of %d non-positive); "
-                                  "L = %d is too large for this grid", status - 1, p->Lp, p->L);
-    if ((rc = launch_synth(p->linv1, p->lpad, p->lpad, p->lpad, p->qt_alt, p->N, p->ld_q, p->qt, p->ld_q, st))) return rc;
-    if ((rc = launch_synth(p->linv1, p->lpad, p->lpad, p->lpad, p->qpt_alt, p->M, p->ld_p, p->qpt, p->ld_p, st))) return rc;
-    // pass 2 (CholeskyQR2): G2 = Q1^T Q1 = L2 L2^T,  Q = Q1 L2^-T;  L^-1 = L2^-1 L1^-1
-    if ((rc = gram_of(p, p->qt, st))) return rc;
-    if ((rc = launch_chol_inv(p->gram, p->lpad, p->Lp, p->lt, p->linv2, p->lpad, p->lpad, p->status, st))) return temd_set_error(rc, "cholesky launch failed");
-    TEMD_CUDA(cudaMemcpyAsync(&status, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TEMD_CUDA(cudaStreamSynchronize(st));
-    if (status != 0) return temd_set_error(-5, "basis_build: second Cholesky pass failed at pivot %d", status - 1);
-    if ((rc = launch_synth(p->linv2, p->lpad, p->lpad, p->lpad, p->qt, p->N, p->ld_q, p->qt_alt, p->ld_q, st))) return rc;
-    if ((rc = launch_synth(p->linv2, p->lpad, p->lpad, p->lpad, p->qpt, p->M, p->ld_p, p->qpt_alt, p->ld_p, st))) return rc;
-    std::swap(p->qt, p->qt_alt);
-    std::swap(p->qpt, p->qpt_alt);
-    if ((rc = launch_matmul_small(p->linv2, p->linv1, p->linv, p->lpad, p->lpad, st))) return temd_set_error(rc, "matmul launch failed");
+    int passes = 2;
+    for (int pass = 0; pass < passes; pass++) {
+        double* cur = (pass == 0) ? p->qt_alt : p->qt;       // pass 0 reads the raw basis from the alt buffers
+        double* curp = (pass == 0) ? p->qpt_alt : p->qpt;
+        if ((rc = gram_of(p, cur, st))) return rc;
+        if ((rc = launch_chol_inv(p->gram, p->lpad, p->Lp, p->lt, p->linv2, p->lpad, p->lpad, p->status, st))) return temd_set_error(rc, "cholesky launch failed");
+        TEMD_CUDA(cudaMemcpyAsync(&status, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TEMD_CUDA(cudaStreamSynchronize(st));
+        if (status != 0 && pass == 0) {
+            double tr[2] = {0.0, 0.0};
+            k_trace_offdiag<<<1, 256, 0, st>>>(p->gram, p->Lp, p->lpad, p->sanity);
+            TEMD_CUDA(cudaMemcpyAsync(tr, p->sanity, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            TEMD_CUDA(cudaStreamSynchronize(st));
+            const double shift = 11.0 * ((double)p->N * p->Lp + (double)p->Lp * (p->Lp + 1)) * 1.1102230246251565e-16 * tr[0];
+            k_add_diag<<<(p->Lp + 127) / 128, 128, 0, st>>>(p->gram, p->lpad, p->Lp, shift);
+            if ((rc = launch_chol_inv(p->gram, p->lpad, p->Lp, p->lt, p->linv2, p->lpad, p->lpad, p->status, st))) return temd_set_error(rc, "cholesky launch failed");
+            TEMD_CUDA(cudaMemcpyAsync(&status, p->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+            TEMD_CUDA(cudaStreamSynchronize(st));
+            passes = 3;
+        }
+        if (status != 0)
+            return temd_set_error(-5, "basis_build: Y0 is numerically rank-deficient (Cholesky pivot %d of %d non-positive in pass %d); "
+                                      "L = %d is too large for this grid", status - 1, p->Lp, pass + 1, p->L);
+        // Y <- L^-1 Y (transposed storage), written to the other buffer pair
+        double* dst = (pass == 0) ? p->qt : p->qt_alt;
+        double* dstp = (pass == 0) ? p->qpt : p->qpt_alt;
+        if ((rc = launch_synth(p->linv2, p->lpad, p->lpad, p->lpad, cur, p->N, p->ld_q, dst, p->ld_q, st))) return rc;
+        if ((rc = launch_synth(p->linv2, p->lpad, p->lpad, p->lpad, curp, p->M, p->ld_p, dstp, p->ld_p, st))) return rc;
+        if (pass > 0) { std::swap(p->qt, p->qt_alt); std::swap(p->qpt, p->qpt_alt); }
+        // accumulate L^-1
+        if (pass == 0) {
+            TEMD_CUDA(cudaMemcpyAsync(p->linv, p->linv2, (size_t)p->lpad * p->lpad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        } else {
+            if ((rc = launch_matmul_small(p->linv2, p->linv, p->linv1, p->lpad, p->lpad, st))) return temd_set_error(rc, "matmul launch failed");
+            std::swap(p->linv, p->linv1);
+        }
+    }
     if (sanity_host != nullptr) {
         // reference's logged check (sph_zonal_mean.py:393-398): Y0inv Y0 = L^-T (Q^T Q) L^T; we report Q^T Q
         if ((rc = gram_of(p, p->qt, st))) return rc;

@@ -222,3 +222,19 @@ def test_large_L_staged_path():
         got = getattr(tem, n)
         got = got() if callable(got) else got
         assert nerr(got, ref[n]) < TOL, (n, nerr(got, ref[n]))
+
+
+def test_ill_conditioned_basis_uses_shifted_cholesky():
+    """cond(Y0) = 3e9 (L close to the grid's resolution): plain CholeskyQR breaks down, the shifted first pass
+    must rescue it; the projector still agrees with pinv to ~cond * eps."""
+    from pytemdiags_b200 import sph_zonal_averager
+    lat, lon = syn.pg2_grid(8)
+    lat_out = np.arange(-89.5, 90, 1.0)
+    L = 100
+    ZM = sph_zonal_averager(lat, lat_out, L, debug=True)
+    ZM.sph_compute_matrices()
+    assert abs(ZM._engine.sanity[0] - (L + 1)) < 1e-8 and abs(ZM._engine.sanity[1]) < 1e-7     # Q^T Q = I
+    A = syn.synth_fields(lat, lon, syn.default_plev(4), 1, seed=5, fields=('ua',))['ua'][0].T.copy()   # (N, 4)
+    Y0, Y0inv, Y0p = oracle.sph_matrices(lat, lat_out, L, method='pinv')
+    assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < 1e-6
+    assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < 1e-4
