@@ -144,6 +144,11 @@ int temd_tracer_epilogue(temd_plan* plan, const temd_tracer_args* args, void* st
  * propagate into its coefficients): returns 0 if all n values are finite, -2 otherwise (synchronises). */
 int temd_check_finite(const double* data, size_t n, void* stream);
 
+/* HOST helper (both pointers are host memory): multi-threaded memcpy used to stage pageable input arrays into
+ * pinned buffers ahead of the asynchronous host->device copy.  No reference counterpart (the reference never leaves
+ * the host). */
+int temd_host_copy(void* dst_host, const void* src_host, size_t bytes, int nthreads);
+
 /* Synthetic benchmark/test fields: out[t][lev][ncol], field 0..4 = ua, va, ta, wap, q. */
 int temd_synth_fields(double* out, int field, int seed, int t0, int nt, int nlev, int ncol, size_t ld,
                       const double* lat_rad, const double* lon_rad, const double* plev_hpa, void* stream);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libtemd.so')
 SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
     'temd_basis_build', 'temd_basis_build_weighted', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
-    'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_synth_fields',
+    'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_host_copy', 'temd_synth_fields',
 )
 
 # order of the output planes written by temd_tem_epilogue (enum TEMD_OUT_* in temd.h)
@@ -75,6 +75,7 @@ def load():
     lib.temd_tem_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), vp]
     lib.temd_tracer_epilogue.argtypes = [vp, C.POINTER(TracerArgs), vp]
     lib.temd_check_finite.argtypes = [vp, sz, vp]
+    lib.temd_host_copy.argtypes = [vp, vp, sz, i]
     lib.temd_synth_fields.argtypes = [vp, i, i, i, i, i, i, sz, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

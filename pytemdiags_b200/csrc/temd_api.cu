@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/temd.h"
@@ -524,5 +525,28 @@ extern "C" int temd_synth_fields(double* out, int field, int seed, int t0, int n
     int rc = launch_synth_fields(out, field, seed, t0, nt, nlev, ncol, ld, lat_rad, lon_rad, plev_hpa,
                                  reinterpret_cast<cudaStream_t>(stream));
     if (rc) return temd_set_error(rc, "synth_fields: kernel launch failed");
+    return 0;
+}
+
+// Host-side helper for ordinary (pageable) input arrays: a multi-threaded memcpy into a pinned staging buffer, so
+// that the host->device copy that follows is a true asynchronous DMA (a single-threaded pageable cudaMemcpy reaches
+// ~10 GB/s on the test box, the pinned DMA 55 GB/s).  Pure host code; no arithmetic.
+extern "C" int temd_host_copy(void* dst, const void* src, size_t bytes, int nthreads) {
+    if (dst == nullptr || src == nullptr) return temd_set_error(-1, "host_copy: null argument");
+    if (nthreads < 1) nthreads = 1;
+    const size_t min_chunk = (size_t)4 << 20;
+    size_t nt = (bytes + min_chunk - 1) / min_chunk;
+    if (nt > (size_t)nthreads) nt = (size_t)nthreads;
+    if (nt <= 1) { memcpy(dst, src, bytes); return 0; }
+    const size_t chunk = ((bytes + nt - 1) / nt + 63) & ~(size_t)63;
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (size_t i = 0; i < nt; i++) {
+        const size_t off = i * chunk;
+        if (off >= bytes) break;
+        const size_t len = (off + chunk <= bytes) ? chunk : bytes - off;
+        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    for (auto& t : th) t.join();
     return 0;
 }

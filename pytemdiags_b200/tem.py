@@ -295,7 +295,7 @@ class TEMDiagnostics:
                 and dims == (self.timename, self.plevname, self.ncolname) and r.is_contiguous()
                 and self.NCOL % 2 == 0 and r.data_ptr() % 16 == 0)
 
-    def _fill(self, dst, var, t0, t1, device):
+    def _fill(self, dst, var, t0, t1, device, slot=None):
         '''Copy time steps [t0, t1) of one input into the staging buffer dst [(t1-t0)*K][ld] (float64, (time, lev,
         ncol) order).  Host arrays in that order go straight into place with one asynchronous copy (a true DMA when
         pinned); other layouts / dtypes / devices are uploaded as they are and permuted on the device.'''
@@ -318,9 +318,35 @@ class TEMDiagnostics:
                 r = np.ascontiguousarray(r)     # strided host slice (time is not the leading dim): pack on the host
             r = torch.from_numpy(r)
         if perm == [0, 1, 2] and not r.is_cuda and r.is_contiguous():
+            if not r.is_pinned() and r.numel() * r.element_size() >= (8 << 20):
+                r = self._stage_pinned(r, slot)
             view.copy_(r, non_blocking=True)
         else:
             view.copy_(r.to(device, non_blocking=True).permute(*perm))
+
+    def _stage_pinned(self, r, slot):
+        '''Pageable host tensor -> pinned staging tensor (cached on the engine, one per (buffer set, field)) by a
+        multi-threaded memcpy in libtemd, so the following H2D copy is an asynchronous DMA.'''
+        import ctypes as C
+        import os
+        eng = self.ZM._engine
+        cache = eng.__dict__.setdefault('_pinned_stage', {})
+        nbytes = r.numel() * r.element_size()
+        ent = cache.get(slot)
+        if ent is None or ent[0].numel() < nbytes:
+            ent = [torch.empty(nbytes, dtype=torch.uint8).pin_memory(), None]
+            cache[slot] = ent
+        if ent[1] is not None:
+            ent[1].synchronize()          # the previous DMA out of this staging buffer must have finished
+        rc = eng.lib.temd_host_copy(C.c_void_p(ent[0].data_ptr()), C.c_void_p(r.data_ptr()), nbytes,
+                                    max(1, min(16, (os.cpu_count() or 2) // 2)))
+        if rc:
+            raise RuntimeError('temd_host_copy failed')
+        ev_ = torch.cuda.Event()
+        out = ent[0][:nbytes].view(r.dtype).view(r.shape)
+        ent[1] = ev_
+        self._pending_stage_events.append(ev_)
+        return out
 
     def _compute_all(self):
         '''_compute_potential_temperature, _decompose_zm_eddy, _compute_fluxes, _compute_derivatives
@@ -406,10 +432,13 @@ class TEMDiagnostics:
                     with torch.cuda.stream(side):
                         if consumed[i % 2] is not None:
                             side.wait_event(consumed[i % 2])
-                        for v, dst in zip(names, bufs[i % 2]):
-                            self._fill(dst, v, t0, t1, dev)
+                        self._pending_stage_events = []
+                        for fi_, (v, dst) in enumerate(zip(names, bufs[i % 2])):
+                            self._fill(dst, v, t0, t1, dev, slot=(i % 2, fi_))
                         ev_ = torch.cuda.Event()
                         ev_.record(side)
+                        for pe in self._pending_stage_events:
+                            pe.record(side)       # marks the end of the DMAs that read the pinned staging buffers
                     filled[i % 2] = ev_
                     return t1
 
