@@ -299,7 +299,9 @@ class TEMDiagnostics:
         '''Copy time steps [t0, t1) of one input into the staging buffer dst [(t1-t0)*K][ld] (float64, (time, lev,
         ncol) order).  Host arrays in that order go straight into place with one asynchronous copy (a true DMA when
         pinned); other layouts / dtypes / devices are uploaded as they are and permuted on the device.'''
-        r = ar.raw(self._vars[var])
+        r = getattr(self, '_whole', {}).get(var)
+        if r is None:
+            r = ar.raw(self._vars[var])
         dims = self._in_dims[var]
         if self.timename in dims:
             sl = [slice(None)] * r.ndim
@@ -323,6 +325,48 @@ class TEMDiagnostics:
             view.copy_(r, non_blocking=True)
         else:
             view.copy_(r.to(device, non_blocking=True).permute(*perm))
+
+    def _upload_whole(self, names, device):
+        '''Host arrays whose time axis is not the leading one cannot be cut into contiguous time slabs.  If the whole
+        record fits comfortably in HBM it is uploaded once in its own layout (flat copies, pinned staging for pageable
+        memory) and the slabs are permuted on the device; otherwise _fill packs each slab on the host.'''
+        self._whole = {}
+        todo = []
+        for v in names:
+            r = ar.raw(self._vars[v])
+            dims = self._in_dims[v]
+            host = isinstance(r, np.ndarray) or not r.is_cuda
+            if host and self.timename in dims and dims[0] != self.timename:
+                todo.append(v)
+        if not todo:
+            return
+        total = sum(int(np.prod(ar.raw(self._vars[v]).shape)) * ar.raw(self._vars[v]).dtype.itemsize
+                    if isinstance(ar.raw(self._vars[v]), np.ndarray)
+                    else ar.raw(self._vars[v]).numel() * ar.raw(self._vars[v]).element_size() for v in todo)
+        free, _ = torch.cuda.mem_get_info(device)
+        if total > 0.4 * free:
+            return
+        for v in todo:
+            r = ar.raw(self._vars[v])
+            if isinstance(r, np.ndarray):
+                if r.dtype.byteorder not in ('=', '|') or not r.flags.writeable or not r.flags.c_contiguous:
+                    r = np.ascontiguousarray(r, dtype=r.dtype.newbyteorder('='))
+                r = torch.from_numpy(r)
+            r = r.contiguous()
+            d = torch.empty(r.shape, dtype=r.dtype, device=device)
+            flat_s, flat_d = r.view(-1), d.view(-1)
+            step = (256 << 20) // r.element_size()
+            for k0, o in enumerate(range(0, flat_s.numel(), step)):
+                piece = flat_s[o:o + step]
+                if not piece.is_pinned():
+                    self._pending_stage_events = []
+                    piece = self._stage_pinned(piece, ('whole', k0 % 2))
+                    flat_d[o:o + step].copy_(piece, non_blocking=True)
+                    for pe in self._pending_stage_events:
+                        pe.record(torch.cuda.current_stream(device))
+                else:
+                    flat_d[o:o + step].copy_(piece, non_blocking=True)
+            self._whole[v] = d
 
     def _stage_pinned(self, r, slot):
         '''Pageable host tensor -> pinned staging tensor (cached on the engine, one per (buffer set, field)) by a
@@ -366,8 +410,11 @@ class TEMDiagnostics:
         nf = len(names)
         ld = N + (N & 1)
         zero_copy = all(self._is_native_device_layout(v, dev) for v in names)
-        budget = self._slab_bytes if self._slab_bytes is not None else ((16 << 30) if zero_copy else (2 << 30))
         fused = eng.lpad <= 408
+        # slab size: in-place device inputs need no staging, so the whole record goes in one launch (best wave
+        # quantisation); host inputs stream through two ~2 GB staging sets
+        budget = self._slab_bytes if self._slab_bytes is not None else (
+            ((1 << 42) if fused else (16 << 30)) if zero_copy else (2 << 30))
         ts = max(1, min(T, int(budget // (nf * 8 * K * N))))
         if not fused:
             ts = max(1, ts // 3)      # the staged path keeps 3 eddies + 3 products of a slab resident
@@ -418,6 +465,7 @@ class TEMDiagnostics:
                 # slab i is computed from the other (no per-slab allocation, no cross-stream allocator traffic)
                 main = torch.cuda.current_stream(dev)
                 side = torch.cuda.Stream(dev)
+                self._upload_whole(names, dev)
                 bufs = [[torch.empty((ts * K, ld), dtype=torch.float64, device=dev) for _ in names] for _ in range(2)]
                 if ld != N:
                     for set_ in bufs:
@@ -454,6 +502,7 @@ class TEMDiagnostics:
                     ev_.record(main)
                     consumed[i % 2] = ev_
                 main.wait_stream(side)
+                self._whole = {}
         eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
         if ntr:
             eng.check_finite(coefq, 'q')

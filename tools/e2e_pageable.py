@@ -23,3 +23,12 @@ for name, host in (('pinned', pinned), ('pageable', pageable)):
         v = tem.vtem()
         torch.cuda.synchronize(); ts.append((time.time() - t0) * 1e3)
     print(name, [round(x) for x in ts], 'GB/s %.1f' % (4 * Te * K * N * 8 / (min(ts) * 1e-3) / 1e9), flush=True)
+# reference-internal layout (ncol, plev, time), pageable
+ref_layout = [np.ascontiguousarray(h.transpose(2, 1, 0)) for h in pageable]
+ts = []
+for rep in range(4):
+    torch.cuda.synchronize(); t0 = time.time()
+    tem = TEMDiagnostics(ref_layout[0], ref_layout[1], ref_layout[2], ref_layout[3], lat, p=plev, L=L, debug_level=0, device=dev)
+    v = tem.vtem()
+    torch.cuda.synchronize(); ts.append((time.time() - t0) * 1e3)
+print('(ncol, plev, time) pageable', [round(x) for x in ts], flush=True)
