@@ -60,7 +60,9 @@ __host__ __device__ inline int eddy_ls(int lpad) {
 }
 
 // GEMM2 inner step for one 16-column chunk: CNT (<= NJ) n8-tiles of this warp, 3 flux products.
-template <int CNT, int NJ, int XF_BYTES>
+// PAIRED: the eddy phase already left v'theta' in the theta tile and u'omega' in the omega tile (see below), so
+// only u'v' is formed here.
+template <int CNT, int NJ, int XF_BYTES, bool PAIRED>
 __device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st, uint32_t qs, uint32_t e_row_off,
                                            const uint32_t (&coff2)[4], int g, int j_begin) {
 #pragma unroll
@@ -70,7 +72,9 @@ __device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st,
         const double ev = lds64(eo + XF_BYTES);
         const double et = lds64(eo + 2 * XF_BYTES);
         const double ew = lds64(eo + 3 * XF_BYTES);
-        const double a_uv = eu * ev, a_uw = eu * ew, a_vt = ev * et;
+        const double a_uv = eu * ev;
+        const double a_uw = PAIRED ? ew : eu * ew;
+        const double a_vt = PAIRED ? et : ev * et;
         const uint32_t bo = qs + (uint32_t)((j_begin * 8 + g) * TILE_ROW_BYTES) + coff2[kk];
         double b[CNT];
 #pragma unroll
@@ -163,7 +167,18 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     // CTA.  Groups are laid out so that the warps sharing an SM sub-partition (warp % 4) belong to
     // different groups and carry complementary GEMM2 loads.
     const int mi = warp / NW2, r_in = warp % NW2;
-    const int f1 = (NW2 == 2) ? r_in * 2 : (NW2 == 4 ? (r_in & 1) * 2 : (r_in >> 1) & 3);
+    // fields: 0 = u, 1 = v, 2 = theta, 3 = omega.  With two fields per warp the pairs are {u, omega} and {v, theta}:
+    // each warp can then form one flux product (u'omega' resp. v'theta') from its own registers in the eddy phase
+    // and store it over the second field's tile, which nobody needs any more; GEMM2 multiplies only u'v'.
+    constexpr bool PAIRED = (NF1 == 2);
+    int fid[NF1];
+    if (PAIRED) {
+        const int pr = (NW2 == 2) ? r_in : (r_in & 1);
+        fid[0] = pr;                 // u or v
+        fid[NF1 - 1] = 3 - pr;       // omega or theta
+    } else {
+        fid[0] = (r_in >> 1) & 3;
+    }
     const int jn1 = (NW2 == 2) ? 0 : (NW2 == 4 ? (r_in >> 1) : (r_in & 1));
     const int wq = (r_in + ((NW2 == 2) ? (mi >> 1) : mi)) % NW2;
     const int grp_bar = 1 + mi, grp_threads = NW2 * 32;
@@ -187,7 +202,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     const int k1c0 = mnmajor_k(t, 0), k1c1 = mnmajor_k(t, 1);
     uint32_t a1_off[NF1];   // GEMM1 A: Cs[(f*BM + mi*8 + g)][.]
 #pragma unroll
-    for (int ff = 0; ff < NF1; ff++) a1_off[ff] = cs_base + (uint32_t)(((f1 + ff) * BM + mi * 8 + g) * p.ls) * 8u;
+    for (int ff = 0; ff < NF1; ff++) a1_off[ff] = cs_base + (uint32_t)((fid[ff] * BM + mi * 8 + g) * p.ls) * 8u;
     uint32_t coff2[4];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) coff2[kk] = kmajor_col_off(g, t, kk);
@@ -238,29 +253,32 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
                         for (int nn = 0; nn < NN1; nn++) dmma(sacc[c][ff][nn][0], sacc[c][ff][nn][1], a[ff], b[c][nn]);
             }
         }
-        // ---------------- eddies, in place over the X tiles ----------------
+        // ---------------- eddies (and, when paired, one flux product), in place over the X tiles ----------------
 #pragma unroll
         for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int ff = 0; ff < NF1; ff++) {
-                const int f = f1 + ff;
-                const double sc = (f == 2) ? tscale : 1.0;
+            for (int nn = 0; nn < NN1; nn++) {
+                const int row = mi * 8 + g;
+                const int col = (jn1 + nn) * 8 + 2 * t;
+                const uint32_t off = swz_off(row, col);
+                double e0[NF1], e1[NF1];
 #pragma unroll
-                for (int nn = 0; nn < NN1; nn++) {
-                    const int row = mi * 8 + g;
-                    const int col = (jn1 + nn) * 8 + 2 * t;
-                    const uint32_t addr = st[c] + f * XF_BYTES + swz_off(row, col);
-                    const double2 x = lds128(addr);
-                    sts128(addr, sc * x.x - sacc[c][ff][nn][0], sc * x.y - sacc[c][ff][nn][1]);
+                for (int ff = 0; ff < NF1; ff++) {
+                    const double sc = (fid[ff] == 2) ? tscale : 1.0;
+                    const double2 x = lds128(st[c] + fid[ff] * XF_BYTES + off);
+                    e0[ff] = sc * x.x - sacc[c][ff][nn][0];
+                    e1[ff] = sc * x.y - sacc[c][ff][nn][1];
                 }
+                sts128(st[c] + fid[0] * XF_BYTES + off, e0[0], e1[0]);
+                if (PAIRED) sts128(st[c] + fid[NF1 - 1] * XF_BYTES + off, e0[0] * e0[NF1 - 1], e1[0] * e1[NF1 - 1]);
             }
         named_bar_sync(grp_bar, grp_threads);
 
         // ---------------- GEMM2: acc += (E_a .* E_b) * QT^T (contraction over the 16 columns) ----------------
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-            if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
-            else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
+            if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES, PAIRED>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
+            else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES, PAIRED>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
         }
         // the E tiles were written through the generic proxy; order them before the next TMA refill
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
