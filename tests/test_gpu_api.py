@@ -238,3 +238,19 @@ def test_ill_conditioned_basis_uses_shifted_cholesky():
     Y0, Y0inv, Y0p = oracle.sph_matrices(lat, lat_out, L, method='pinv')
     assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < 1e-6
     assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < 1e-4
+
+
+def test_many_rows_and_fine_zm_grid():
+    """rows = time*lev = 72,000 (> 65,535: no 16-bit grid-dimension limits anywhere) and zm_dlat = 0.5 (M = 360)."""
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon = syn.pg2_grid(4)
+    K, T, L = 72, 1000, 10
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=11)
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=L, dims=('time', 'lev', 'ncol'),
+                         debug_level=0, zm_dlat=0.5)
+    ref = _ref(f, plev, lat, L, zm_dlat=0.5)
+    assert tem.ZM_N == 360
+    for n in oracle.TEM_OUTPUTS:
+        assert nerr(getattr(tem, n)(), ref[n]) < TOL, n
+    assert nerr(tem.up, ref['up']) < TOL          # on-demand native eddy over 72,000 rows
