@@ -37,7 +37,10 @@ def _worker(rank, world, port, T, q):
 def test_gather_time_sharded_gloo(T):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + T) % 2000
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, T, q)) for r in range(2)]
     for p in procs:
         p.start()

@@ -12,8 +12,12 @@ def test_sharded_tem_single_rank_nccl():
     import torch.distributed as dist
     from pytemdiags_b200 import TEMDiagnostics, synthetic as syn
     from pytemdiags_b200.distributed import ShardedTEM, shard_bounds
-    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    os.environ.setdefault('MASTER_PORT', '29531')
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
     created = False
     if not dist.is_initialized():
         dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda:0'))
