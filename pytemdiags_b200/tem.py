@@ -383,7 +383,7 @@ class TEMDiagnostics:
         if ent[1] is not None:
             ent[1].synchronize()          # the previous DMA out of this staging buffer must have finished
         rc = eng.lib.temd_host_copy(C.c_void_p(ent[0].data_ptr()), C.c_void_p(r.data_ptr()), nbytes,
-                                    max(1, min(16, (os.cpu_count() or 2) // 2)))
+                                    max(1, min(8, (os.cpu_count() or 2) // 2)))
         if rc:
             raise RuntimeError('temd_host_copy failed')
         ev_ = torch.cuda.Event()
