@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtemd.so')
+LIB_PATH = os.environ.get('TEMD_LIB', os.path.join(_HERE, 'libtemd.so'))   # TEMD_LIB: A/B-test another build
 
 # every symbol include/temd.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
