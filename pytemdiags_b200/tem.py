@@ -737,5 +737,81 @@ class TEMDiagnostics:
         '''eastward-wind tendency due to TEM upward advection [m/s2] (tem_diagnostics.py:783-797)'''
         return self._result('utendwtem')
 
-    def to_netcdf(self, *a, **k):
-        raise NotImplementedError('netCDF output is outside the hot path of this build (SURVEY.md §2 row 10)')
+    # ---- file output (tem_diagnostics.py:995-1103).  The reference writes through xarray/netCDF4; neither is a
+    #      dependency here, so the files are NetCDF-3 (64-bit offset) written with scipy.io.netcdf_file: same file
+    #      names, variable names and dims ('lat', plev, time) / ('ncol', plev, time).
+    def _write_nc(self, path, output):
+        from scipy.io import netcdf_file
+        def _np(x):
+            v = x.values if ar.is_dataarray(x) else x
+            return v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        with netcdf_file(path, 'w', version=2) as nc:
+            nc.createDimension('lat', self.ZM_N)
+            nc.createDimension(self.plevname, self.NLEV)
+            nc.createDimension(self.timename, self.NT)
+            for dim, vals in (('lat', self._lat_zm), (self.plevname, self.plev), (self.timename, self.time)):
+                vals = np.asarray(vals)
+                if vals.dtype.kind in 'iuf':
+                    v = nc.createVariable(dim, 'f8', (dim,))
+                    v[:] = vals.astype(np.float64)
+            for name, val in output.items():
+                a_ = _np(val)
+                if a_.shape[0] == self.ZM_N:
+                    dims = ('lat', self.plevname, self.timename)
+                else:
+                    if self.ncolname not in nc.dimensions:
+                        nc.createDimension(self.ncolname, self.NCOL)
+                    dims = (self.ncolname, self.plevname, self.timename)
+                v = nc.createVariable(name, a_.dtype.char if a_.dtype.kind == 'f' else 'f8', dims)
+                v[:] = a_
+        return path
+
+    def to_netcdf(self, loc=None, prefix=None, include_attrs=False):
+        '''Saves all TEM quantities to `{prefix_}TEM_{grid}_{gridout}_L{L}.nc` under `loc` (tem_diagnostics.py:995-1041).
+        include_attrs=True also writes the intermediates (zonal means, eddies, fluxes, derivatives).'''
+        import os
+        loc = os.getcwd() if loc is None else loc
+        results = {n: getattr(self, n)() for n in _METHODS}
+        if include_attrs:
+            attrs = {n: getattr(self, n) for n in ('ub', 'up', 'vb', 'vp', 'thetab', 'thetap', 'wapb', 'upvp', 'upvpb',
+                                                   'upwapp', 'upwappb', 'vptp', 'vptpb', 'dub_dp', 'dthetab_dp', 'ubcoslat',
+                                                   'dubcoslat_dlat', 'psi', 'psicoslat', 'dpsicoslat_dlat', 'dpsi_dp',
+                                                   'int_vbdp')}
+            attrs['wawpp'] = self.wapp          # key spelled as in the reference (:1011)
+            output = dict(attrs, **results)
+        else:
+            output = results
+        prefix = '{}_'.format(prefix) if prefix is not None else ''
+        filename = '{}TEM_{}_{}_L{}.nc'.format(prefix, self.ZM.grid_name, self.ZM.grid_out_name, self.L)
+        self._out_file = '{}/{}'.format(loc, filename)
+        self._write_nc(self._out_file, output)
+        self._log('wrote TEM data to {}'.format(self._out_file))
+        return self._out_file
+
+    @property
+    def q_out_file(self):
+        if len(self._q_out_file) == 0:
+            warnings.warn('\'q_out_file\' is emtpy; no tracers currently present')
+        elif self._q_out_file.count(None) == self.ntrac:
+            warnings.warn('\'q_out_file\' is not set until q_to_netcdf() is called')
+        return self._q_out_file
+
+    def q_to_netcdf(self, loc=None, qi=None, prefix=None, include_attrs=False):
+        '''One file per tracer, `{prefix_}TEM_{grid}_{gridout}_L{L}_TRACER-{name}.nc` (tem_diagnostics.py:1045-1103).'''
+        import os
+        assert self.ntrac > 0, 'No tracers to output (argument `q` not passed at object construction)'
+        loc = os.getcwd() if loc is None else loc
+        prefix = '{}_'.format(prefix) if prefix is not None else ''
+        names = [getattr(qq, 'name', None) if ar.is_dataarray(qq) else None for qq in self.q]
+        names = [n if n is not None else 'q{}'.format(i) for i, n in enumerate(names)]
+        for i in (range(self.ntrac) if qi is None else [qi]):
+            output = {"etfy": self.etfy(i), "etfz": self.etfz(i), "etdiv": self.etdiv(i), "qtendetfd": self.qtendetfd(i),
+                      "qtendvtem": self.qtendvtem(i), "qtendwtem": self.qtendwtem(i)}
+            if include_attrs:
+                output.update({"qpvp": self.qpvp[i], "qpwapp": self.qpwapp[i], "qpvpb": self.qpvpb[i],
+                               "qpwappb": self.qpwappb[i], "dqp_dp": self.dqb_dp[i], "qbcoslat": self.qbcoslat[i],
+                               "dqbcoslat_dlat": self.dqbcoslat_dlat[i]})
+            filename = '{}TEM_{}_{}_L{}_TRACER-{}.nc'.format(prefix, self.ZM.grid_name, self.ZM.grid_out_name, self.L, names[i])
+            self._q_out_file[i] = '{}/{}'.format(loc, filename)
+            self._write_nc(self._q_out_file[i], output)
+        return self._q_out_file

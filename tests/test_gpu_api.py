@@ -254,3 +254,27 @@ def test_many_rows_and_fine_zm_grid():
     for n in oracle.TEM_OUTPUTS:
         assert nerr(getattr(tem, n)(), ref[n]) < TOL, n
     assert nerr(tem.up, ref['up']) < TOL          # on-demand native eddy over 72,000 rows
+
+
+def test_to_netcdf_roundtrip(tmp_path):
+    """to_netcdf / q_to_netcdf (tem_diagnostics.py:995-1103): same file names and variables, NetCDF-3 via SciPy."""
+    from scipy.io import netcdf_file
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon = syn.pg2_grid(4)
+    K, T, L = 5, 2, 10
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=12, fields=('ua', 'va', 'ta', 'wap', 'q'))
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, q=f['q'], L=L, dims=('time', 'lev', 'ncol'),
+                         debug_level=0, grid_name='ne4pg2')
+    path = tem.to_netcdf(loc=str(tmp_path), prefix='x', include_attrs=True)
+    assert path.endswith('x_TEM_ne4pg2_1.0deg_L10.nc') and tem.out_file == path
+    with netcdf_file(path, 'r', mmap=False) as nc:
+        for n in oracle.TEM_OUTPUTS:
+            assert nc.variables[n].dimensions == ('lat', 'plev', 'time')
+            assert np.array_equal(nc.variables[n][:], getattr(tem, n)())
+        assert nc.variables['up'].dimensions == ('ncol', 'plev', 'time')
+        assert np.array_equal(nc.variables['lat'][:], tem.lat)
+    qpaths = tem.q_to_netcdf(loc=str(tmp_path))
+    assert qpaths[0].endswith('TEM_ne4pg2_1.0deg_L10_TRACER-q0.nc')
+    with netcdf_file(qpaths[0], 'r', mmap=False) as nc:
+        assert np.array_equal(nc.variables['etdiv'][:], tem.etdiv())

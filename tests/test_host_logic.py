@@ -111,3 +111,19 @@ def test_dataarray_inputs_any_dim_order(stubbed):
     assert t.ntrac == 2
     with pytest.raises(RuntimeError, match='qi must be passed'):
         t._qi(None, 'etfy')
+
+
+def test_format_latlon_data_column_order():
+    """lat-major ravel, ncol = ilat*NLON + ilon (tem_util.py:331); matches synthetic.latlon_grid (config 4's layout)."""
+    from pytemdiags_b200.util import format_latlon_data
+    lat = np.linspace(-90, 90, 5)
+    lon = np.arange(8) * 45.0
+    A = np.arange(3 * 5 * 8, dtype=np.float64).reshape(3, 5, 8)          # (time, lat, lon)
+    A2, la, lo = format_latlon_data(A, lat, lon)
+    assert A2.shape == (3, 40) and A2[1, 2 * 8 + 3] == A[1, 2, 3]
+    glat, glon = syn.latlon_grid(5, 8)
+    assert np.array_equal(la, glat) and np.array_equal(lo, glon)
+    B2, _, _ = format_latlon_data(A.transpose(2, 0, 1), lat, lon, lat_axis=2, lon_axis=0)
+    assert np.array_equal(B2, A2)
+    with pytest.raises(RuntimeError):
+        format_latlon_data(A, lat[:-1], lon)
