@@ -1,0 +1,65 @@
+"""GPU: seeded random small problems (arbitrary latitudes, odd/tiny column counts, K = 2, T = 1, L = 0, random dim
+orders, float32, reversed pressure) through the public API against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def nerr(x, ref):
+    return float(np.abs(np.asarray(x) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    N = int(rng.choice([17, 20, 33, 64, 95, 128, 250, 517, 1000]))
+    Lmax = max(0, min(40, N // 6))
+    L = int(rng.integers(0, Lmax + 1))
+    K = int(rng.integers(2, 9))
+    T = int(rng.integers(1, 5))
+    lat = np.rad2deg(np.arcsin(rng.uniform(-0.995, 0.995, N)))          # area-uniform random latitudes
+    plev = np.geomspace(5.0, 1000.0, K) * rng.uniform(0.9, 1.1, K)     # well separated, so d(theta)/dp stays away from 0
+    if rng.random() < 0.5:
+        plev = plev[::-1].copy()
+    s = (np.sort(plev) / 1000.0)
+    base = {}
+    shape = (N, K, T)
+    lev_pos = np.argsort(np.argsort(plev))                              # rank of each level in ascending order
+    ta = 210 + 75 * (plev / 1000.0)[None, :, None] ** 0.19 * np.cos(np.deg2rad(lat))[:, None, None] ** 2 \
+        + 0.05 * rng.standard_normal(shape)
+    base['ta'] = ta
+    base['ua'] = 20 * rng.standard_normal(shape)
+    base['va'] = 3 * rng.standard_normal(shape)
+    base['wap'] = 0.05 * rng.standard_normal(shape)
+    order = list(rng.permutation(3))
+    dims_all = ('ncol', 'plev', 'time')
+    dims = tuple(dims_all[i] for i in order)
+    dtype = np.float32 if rng.random() < 0.25 else np.float64
+    fields = {k: np.ascontiguousarray(np.transpose(v, order)).astype(dtype) for k, v in base.items()}
+    ref_in = {k: np.transpose(fields[k].astype(np.float64), np.argsort(order)) for k in base}
+    return lat, plev, L, dims, dtype, fields, ref_in
+
+
+@pytest.mark.parametrize('seed', list(range(24)))
+def test_random_small_problem(seed):
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, plev, L, dims, dtype, fields, ref_in = _random_case(seed)
+    Y0 = oracle.sph_basis(lat, L)
+    sv = np.linalg.svd(Y0, compute_uv=False)
+    if sv[0] / sv[-1] > 1e4:
+        pytest.skip('ill-conditioned random latitude set (cond %.1e)' % (sv[0] / sv[-1]))
+    tem = TEMDiagnostics(fields['ua'], fields['va'], fields['ta'], fields['wap'], lat, p=plev, L=L, dims=dims, debug_level=0)
+    ref = oracle.tem_suite(ref_in['ua'], ref_in['va'], ref_in['ta'], ref_in['wap'], plev, lat, L=L)
+    alt = oracle.tem_suite(ref_in['ua'], ref_in['va'], ref_in['ta'], ref_in['wap'], plev, lat, L=L, literal=False)
+    for n in oracle.TEM_OUTPUTS:
+        got = getattr(tem, n)()
+        assert got.dtype == dtype and got.shape == ref[n].shape
+        # tolerance: 1e-9, widened by the conditioning of this random problem as seen by the oracle itself
+        # (literal vs factored association of the reference formula)
+        tol = (2e-5 if dtype == np.float32 else 1e-9) + 50 * nerr(alt[n], ref[n])
+        assert nerr(got.astype(np.float64), ref[n]) < tol, (seed, n, nerr(got.astype(np.float64), ref[n]), tol)
+    if dtype == np.float64:
+        for n in ('ub', 'thetab', 'vptpb', 'psi', 'int_vbdp'):
+            assert nerr(getattr(tem, n), ref[n]) < 1e-9, (seed, n)
