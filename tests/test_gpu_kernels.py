@@ -97,3 +97,23 @@ def test_epilogue(ne, L, K, T):
     for n, v in out.items():
         got = v.cpu().numpy().transpose(2, 1, 0)
         assert nerr(got, ref[n]) < 1e-12, n
+
+
+def test_run_to_run_reproducible():
+    """Split-K partials are reduced in a fixed order (no atomics): two runs give bit-identical coefficients."""
+    import torch
+    lat, lon = syn.pg2_grid(16)
+    K, T, L = 16, 6, 100
+    plev = syn.default_plev(K)
+    eng = _engine(lat, oracle.zm_latitudes(1), L)
+    f = syn.synth_fields(lat, lon, plev, T, seed=7)
+    N = lat.shape[0]
+    xs = [torch.as_tensor(f[n].reshape(T * K, N)).cuda() for n in ('ua', 'va', 'ta', 'wap')]
+    sc = torch.ones(K, dtype=torch.float64, device='cuda')
+    runs = []
+    for _ in range(3):
+        c4 = eng.project(xs, lev_scale=sc, scale_field=2, nlev=K)
+        cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, sc, K)
+        runs.append((c4.clone(), cf.clone()))
+    for c4, cf in runs[1:]:
+        assert torch.equal(c4, runs[0][0]) and torch.equal(cf, runs[0][1])
