@@ -13,7 +13,9 @@
  *     except temd_basis_build (one status read-back) and temd_check_finite;
  *   - return value 0 = ok, < 0 = argument / numerical error, > 0 = cudaError_t;
  *     temd_last_error() returns a thread-local description.
- *   - inputs are borrowed read-only; the plan owns only its basis and split-K workspace.
+ *   - inputs are borrowed read-only; the plan owns only its basis and one split-K workspace per stream: entry points
+ *     are stream-ordered and re-entrant per (device, stream); they run on the plan's device and restore the caller's
+ *     current device before returning.
  */
 #ifndef TEMD_H
 #define TEMD_H
@@ -141,13 +143,26 @@ enum {
 int temd_tracer_epilogue(temd_plan* plan, const temd_tracer_args* args, void* stream);
 
 /* NaN screen of sph_zonal_mean.py:219-221 done on the small coefficient block (NaNs in a field
- * propagate into its coefficients): returns 0 if all n values are finite, -2 otherwise (synchronises). */
+ * propagate into its coefficients): returns 0 if all n values are finite, -2 if a NaN was found, -6 if only
+ * infinities were found (the reference screens NaN only).  Runs on the device that owns `data`; synchronises. */
 int temd_check_finite(const double* data, size_t n, void* stream);
 
 /* HOST helper (both pointers are host memory): multi-threaded memcpy used to stage pageable input arrays into
  * pinned buffers ahead of the asynchronous host->device copy.  No reference counterpart (the reference never leaves
  * the host). */
 int temd_host_copy(void* dst_host, const void* src_host, size_t bytes, int nthreads);
+
+/* Multi-GPU: time steps never interact (sph_zonal_mean.py:244-251, tem_util.py:154,192,232), so each
+ * process owns a time slab and the only exchange is ONE all-gather of the stacked output planes at the end.
+ * libnccl.so.2 is resolved at run time (dlopen); without it these three calls return -7 and everything else works.
+ *   temd_comm_unique_id : rank 0 makes the 128-byte id and ships it to the other ranks by any side channel;
+ *   temd_comm_init      : collective over all ranks (ncclCommInitRank) on `device`;
+ *   temd_allgather_outputs : recv[r*count .. (r+1)*count) = rank r's send[0 .. count), enqueued on `stream`. */
+typedef struct temd_comm temd_comm;
+int temd_comm_unique_id(char* id128_host);
+int temd_comm_init(int device, int nranks, int rank, const char* id128_host, temd_comm** comm);
+int temd_comm_destroy(temd_comm* comm);
+int temd_allgather_outputs(temd_comm* comm, const double* send, double* recv, size_t count, void* stream);
 
 /* Synthetic benchmark/test fields: out[t][lev][ncol], field 0..4 = ua, va, ta, wap, q. */
 int temd_synth_fields(double* out, int field, int seed, int t0, int nt, int nlev, int ncol, size_t ld,

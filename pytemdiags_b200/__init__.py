@@ -5,6 +5,6 @@ reference's constructor arguments, methods and error behaviour (PyTEMDiags/__ini
 arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of `include/temd.h`.
 """
 from .zonal import sph_zonal_averager  # noqa: F401
-from .tem import TEMDiagnostics  # noqa: F401
+from .tem import TEMDiagnostics, release_host_staging  # noqa: F401
 
 __version__ = '0.1'

@@ -14,6 +14,7 @@ SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
     'temd_basis_build', 'temd_basis_build_weighted', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
     'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_host_copy', 'temd_synth_fields',
+    'temd_comm_unique_id', 'temd_comm_init', 'temd_comm_destroy', 'temd_allgather_outputs',
 )
 
 # order of the output planes written by temd_tem_epilogue (enum TEMD_OUT_* in temd.h)
@@ -77,6 +78,10 @@ def load():
     lib.temd_check_finite.argtypes = [vp, sz, vp]
     lib.temd_host_copy.argtypes = [vp, vp, sz, i]
     lib.temd_synth_fields.argtypes = [vp, i, i, i, i, i, i, sz, vp, vp, vp, vp]
+    lib.temd_comm_unique_id.argtypes = [C.c_char_p]
+    lib.temd_comm_init.argtypes = [i, i, i, C.c_char_p, C.POINTER(vp)]
+    lib.temd_comm_destroy.argtypes = [vp]
+    lib.temd_allgather_outputs.argtypes = [vp, vp, vp, sz, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('temd_last_error',):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libtemd.so')
 SOURCES = ['temd_api.cu', 'temd_project.cu', 'temd_basis.cu', 'temd_synth.cu', 'temd_synth_res.cu', 'temd_eddy.cu',
-           'temd_epilogue.cu', 'temd_fields.cu']
+           'temd_epilogue.cu', 'temd_fields.cu', 'temd_comm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
         if pr.returncode != 0:
             raise RuntimeError('nvcc failed on %s' % src)
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     subprocess.check_call(cmd)
     return LIB
 

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -30,6 +32,21 @@ int temd_set_error(int code, const char* fmt, ...) {
             return temd_set_error((int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
                                   __FILE__, __LINE__);                                               \
     } while (0)
+
+// Every entry point runs on the plan's device and leaves the caller's current device untouched.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else if (err == cudaSuccess) prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define TEMD_ON_DEVICE(dev)                 \
+    DeviceGuard guard__(dev);               \
+    TEMD_CUDA(guard__.err)
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -70,12 +87,16 @@ int make_tma_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1
     return 0;
 }
 
+// flag bit 0: a NaN was seen, bit 1: an infinity was seen
 __global__ void k_check_finite(const double* __restrict__ d, size_t n, int* __restrict__ flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     int bad = 0;
-    for (; i < n; i += stride) bad |= !isfinite(d[i]);
-    if (bad) *flag = 1;
+    for (; i < n; i += stride) {
+        const double v = d[i];
+        bad |= (v != v) ? 1 : (isinf(v) ? 2 : 0);
+    }
+    if (bad) atomicOr(flag, bad);
 }
 
 __global__ void k_trace_offdiag(const double* __restrict__ G, int n, int ld, double* __restrict__ out2) {
@@ -157,21 +178,27 @@ struct temd_plan {
     double *linv, *linv1, *linv2, *gram, *lt;   // [lpad][lpad] each
     double *rec_a, *rec_b;   // recurrence coefficients [L+1]
     double *x, *x_out;       // copies of the node coordinates (for exports)
-    double *work;            // split-K partials
-    size_t work_doubles;
+    std::mutex* work_mu;     // split-K partials: one workspace per stream, so a plan is re-entrant per (device, stream)
+    std::map<cudaStream_t, std::pair<double*, size_t>>* work;
     int* status;
     double* sanity;
     bool built;
     bool weighted;   // deprecated quadrature inverse Y0inv = Y0^T diag(w): qt = raw basis (synthesis), qt_alt = weighted (projection)
 };
 
-static int ensure_work(temd_plan* p, size_t doubles) {
-    if (doubles <= p->work_doubles) return 0;
-    if (p->work) TEMD_CUDA(cudaFree(p->work));
-    p->work = nullptr;
-    p->work_doubles = 0;
-    TEMD_CUDA(cudaMalloc(&p->work, doubles * sizeof(double)));
-    p->work_doubles = doubles;
+// Split-K workspace of `stream` (grown on demand).  Work already enqueued on that stream may still use the old
+// buffer when it grows: cudaFree synchronises the device before releasing it.
+static int ensure_work(temd_plan* p, cudaStream_t stream, size_t doubles, double** out) {
+    std::lock_guard<std::mutex> lock(*p->work_mu);
+    auto& w = (*p->work)[stream];
+    if (doubles > w.second) {
+        if (w.first) TEMD_CUDA(cudaFree(w.first));
+        w.first = nullptr;
+        w.second = 0;
+        TEMD_CUDA(cudaMalloc(&w.first, doubles * sizeof(double)));
+        w.second = doubles;
+    }
+    *out = w.first;
     return 0;
 }
 
@@ -186,12 +213,14 @@ extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_
     if (ncol < 1 || L < 0 || nlat_out < 1) return temd_set_error(-1, "plan_create: bad sizes (ncol %d, L %d, M %d)", ncol, L, nlat_out);
     if (L + 1 > 1024) return temd_set_error(-1, "plan_create: L = %d exceeds the supported maximum 1023", L);
     if (L + 1 > ncol) return temd_set_error(-1, "plan_create: L+1 = %d exceeds ncol = %d (Y0 would be rank-deficient)", L + 1, ncol);
-    TEMD_CUDA(cudaSetDevice(device));
+    TEMD_ON_DEVICE(device);
     cudaDeviceProp prop;
     TEMD_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return temd_set_error(-4, "libtemd is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
     temd_plan* p = new temd_plan();
     memset(p, 0, sizeof(*p));
+    p->work_mu = new std::mutex();
+    p->work = new std::map<cudaStream_t, std::pair<double*, size_t>>();
     p->dev = device; p->N = ncol; p->L = L; p->Lp = L + 1; p->M = nlat_out;
     p->lpad = (int)round_up(L + 1, 8);
     p->sms = prop.multiProcessorCount;
@@ -217,11 +246,14 @@ extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_
 
 extern "C" int temd_plan_destroy(temd_plan* p) {
     if (p == nullptr) return 0;
-    cudaSetDevice(p->dev);
+    DeviceGuard guard(p->dev);
     double* bufs[] = {p->qt, p->qt_alt, p->qpt, p->qpt_alt, p->linv, p->linv1, p->linv2, p->gram, p->lt,
-                      p->rec_a, p->rec_b, p->x, p->x_out, p->work, p->sanity};
+                      p->rec_a, p->rec_b, p->x, p->x_out, p->sanity};
     for (double* b : bufs) if (b) cudaFree(b);
+    if (p->work) for (auto& kv : *p->work) if (kv.second.first) cudaFree(kv.second.first);
     if (p->status) cudaFree(p->status);
+    delete p->work;
+    delete p->work_mu;
     delete p;
     return 0;
 }
@@ -234,16 +266,17 @@ static int gram_of(temd_plan* p, const double* basis, cudaStream_t st) {
     const int tiles = (p->Lp + 127) / 128;
     const int nchunks = (p->N + 15) / 16;
     const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 512);
-    int rc = ensure_work(p, project_workspace_doubles(1, p->Lp, p->lpad, nsplit));
+    double* work = nullptr;
+    int rc = ensure_work(p, st, project_workspace_doubles(1, p->Lp, p->lpad, nsplit), &work);
     if (rc) return rc;
     const double* xs[1] = {basis};
-    return launch_project(xs, 1, p->Lp, p->N, p->ld_q, basis, p->lpad, p->ld_q, p->gram, p->work, nsplit, nullptr, -1, 1, st);
+    return launch_project(xs, 1, p->Lp, p->N, p->ld_q, basis, p->lpad, p->ld_q, p->gram, work, nsplit, nullptr, -1, 1, st);
 }
 
 extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_out, double* sanity_host, void* stream) {
     if (p == nullptr || x == nullptr || x_out == nullptr) return temd_set_error(-1, "basis_build: null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     // recurrence coefficients: Y_l = a_l x Y_{l-1} - b_l Y_{l-2}
     std::vector<double> ra(p->lpad, 0.0), rb(p->lpad, 0.0);
     const double PI = 3.141592653589793238462643383279502884;
@@ -321,7 +354,7 @@ extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_o
 extern "C" int temd_basis_build_weighted(temd_plan* p, const double* x, const double* x_out, const double* w, void* stream) {
     if (p == nullptr || x == nullptr || x_out == nullptr || w == nullptr) return temd_set_error(-1, "basis_build_weighted: null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     std::vector<double> ra(p->lpad, 0.0), rb(p->lpad, 0.0);
     const double PI = 3.141592653589793238462643383279502884;
     ra[0] = std::sqrt(1.0 / (4.0 * PI));
@@ -350,7 +383,7 @@ extern "C" int temd_basis_build_weighted(temd_plan* p, const double* x, const do
 extern "C" int temd_basis_export(temd_plan* p, double* Y0, double* Y0inv, double* Y0p, void* stream) {
     if (p == nullptr || !p->built) return temd_set_error(-1, "basis_export: basis not built");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     int rc;
     dim3 tb(32, 8);
     if (p->weighted) {
@@ -397,29 +430,30 @@ extern "C" int temd_project(temd_plan* p, const double* const* fields_host, int 
         return temd_set_error(-1, "project: bad arguments (nfields %d, rows %d, ld %zu, ncol %d)", nfields, rows, ld, p->N);
     if (lev_scale != nullptr && nlev < 1) return temd_set_error(-1, "project: nlev must be >= 1 with lev_scale");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     int ntb, lblocks;
     project_lblocks(p->lpad, &ntb, &lblocks);
     const int tiles = ((rows + 127) / 128) * nfields;
     const int nchunks = (p->N + 15) / 16;
     const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 64);
-    int rc = ensure_work(p, project_workspace_doubles(nfields, rows, p->lpad, nsplit));
+    double* work = nullptr;
+    int rc = ensure_work(p, st, project_workspace_doubles(nfields, rows, p->lpad, nsplit), &work);
     if (rc) return rc;
-    return launch_project(fields_host, nfields, rows, p->N, ld, p->weighted ? p->qt_alt : p->qt, p->lpad, p->ld_q, coef, p->work, nsplit,
+    return launch_project(fields_host, nfields, rows, p->N, ld, p->weighted ? p->qt_alt : p->qt, p->lpad, p->ld_q, coef, work, nsplit,
                           lev_scale, scale_field, nlev < 1 ? 1 : nlev, st);
 }
 
 extern "C" int temd_synth_out(temd_plan* p, const double* coef, int rows, double* out, size_t ld_out, void* stream) {
     if (p == nullptr || !p->built) return temd_set_error(-1, "synth_out: basis not built");
     if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->M) return temd_set_error(-1, "synth_out: bad arguments");
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     return launch_synth(coef, rows, p->lpad, p->lpad, p->qpt, p->M, p->ld_p, out, ld_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int temd_synth_native(temd_plan* p, const double* coef, int rows, double* out, size_t ld_out, void* stream) {
     if (p == nullptr || !p->built) return temd_set_error(-1, "synth_native: basis not built");
     if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->N) return temd_set_error(-1, "synth_native: bad arguments");
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     static const bool use_res = [] { const char* e = getenv("TEMD_SYNTH_RESIDENT"); return !(e && atoi(e) == 0); }();
     if (use_res) {
         const int rc = launch_synth_resident(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, p->sms,
@@ -432,11 +466,20 @@ extern "C" int temd_synth_native(temd_plan* p, const double* coef, int rows, dou
 
 extern "C" int temd_check_finite(const double* data, size_t n, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // one persistent 4-byte flag per device (never freed: cudaFree would synchronise the whole device)
-    static int* flags[64] = {nullptr};
-    int dev = 0;
-    TEMD_CUDA(cudaGetDevice(&dev));
+    if (data == nullptr) return temd_set_error(-1, "check_finite: null argument");
+    // run on the device that owns `data`, whatever the caller's current device is
+    cudaPointerAttributes attr;
+    TEMD_CUDA(cudaPointerGetAttributes(&attr, data));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+        return temd_set_error(-1, "check_finite: data must be a device pointer");
+    const int dev = attr.device;
     if (dev < 0 || dev >= 64) return temd_set_error(-1, "check_finite: device index out of range");
+    TEMD_ON_DEVICE(dev);
+    // one persistent 4-byte flag per device (never freed: cudaFree would synchronise the whole device); calls on one
+    // device are serialised by the mutex because the flag is shared
+    static int* flags[64] = {nullptr};
+    static std::mutex mu[64];
+    std::lock_guard<std::mutex> lock(mu[dev]);
     if (flags[dev] == nullptr) TEMD_CUDA(cudaMalloc(&flags[dev], sizeof(int)));
     int* flag = flags[dev];
     TEMD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -446,7 +489,8 @@ extern "C" int temd_check_finite(const double* data, size_t n, void* stream) {
     cudaError_t e = cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return temd_set_error((int)e, "check_finite: %s", cudaGetErrorString(e));
-    if (h) return temd_set_error(-2, "non-finite values (NaN/Inf) found");
+    if (h & 1) return temd_set_error(-2, "NaN values found");
+    if (h & 2) return temd_set_error(-6, "infinite values found (no NaN)");
     return 0;
 }
 
@@ -461,13 +505,14 @@ extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const doubl
     if (!eddy_supported(p->lpad)) return temd_set_error(-1, "eddy_flux_project: L = %d too large for the fused kernel (max 407)", p->L);
     if (p->weighted) return temd_set_error(-1, "eddy_flux_project: not available with the quadrature-weights inverse (TEMDiagnostics never uses it)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     const int nchunks = (p->N + 15) / 16;
     const int nsplit = eddy_pick_split(rows, p->lpad, nchunks, p->sms);
-    int rc = ensure_work(p, eddy_workspace_doubles(rows, p->lpad, nsplit));
+    double* work = nullptr;
+    int rc = ensure_work(p, st, eddy_workspace_doubles(rows, p->lpad, nsplit), &work);
     if (rc) return rc;
     const double* x4[4] = {u, v, t, w};
-    return launch_eddy_flux_project(x4, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef4, coef_flux, p->work, nsplit,
+    return launch_eddy_flux_project(x4, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef4, coef_flux, work, nsplit,
                                     lev_scale, nlev, st);
 }
 
@@ -475,7 +520,7 @@ extern "C" int temd_tem_epilogue(temd_plan* p, const temd_epilogue_args* args, v
     if (p == nullptr || args == nullptr) return temd_set_error(-1, "tem_epilogue: null argument");
     if (args->nlev < 2 || args->nlat < 2 || args->nt < 1 || args->ld < (size_t)args->nlat)
         return temd_set_error(-1, "tem_epilogue: need nlev >= 2, nlat >= 2, nt >= 1 (np.gradient needs two points)");
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     EpilogueArgs w;
     w.a = *args;
     int rc = launch_tem_epilogue(w, reinterpret_cast<cudaStream_t>(stream));
@@ -488,7 +533,7 @@ extern "C" int temd_eddy_native(temd_plan* p, const double* x, size_t ld_x, cons
     if (p == nullptr || !p->built) return temd_set_error(-1, "eddy_native: basis not built");
     if (!x || !coef || !out || rows < 1 || ld_x < (size_t)p->N || ld_out < (size_t)p->N) return temd_set_error(-1, "eddy_native: bad arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     int rc = launch_synth(coef, rows, p->lpad, p->lpad, p->qt, p->N, p->ld_q, out, ld_out, st);
     if (rc) return rc;
     dim3 grid((p->N + 255) / 256, rows < 32768 ? rows : 32768);
@@ -512,7 +557,7 @@ extern "C" int temd_tracer_epilogue(temd_plan* p, const temd_tracer_args* args, 
     if (p == nullptr || args == nullptr) return temd_set_error(-1, "tracer_epilogue: null argument");
     if (args->nlev < 2 || args->nlat < 2 || args->nt < 1 || args->ld < (size_t)args->nlat)
         return temd_set_error(-1, "tracer_epilogue: need nlev >= 2, nlat >= 2, nt >= 1");
-    TEMD_CUDA(cudaSetDevice(p->dev));
+    TEMD_ON_DEVICE(p->dev);
     int rc = launch_tracer_epilogue(*args, reinterpret_cast<cudaStream_t>(stream));
     if (rc) return temd_set_error(rc, "tracer_epilogue: kernel launch failed");
     return 0;

@@ -91,10 +91,16 @@ __device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st,
     }
 }
 
+// Producer warps: with 16 consumer warps a single extra warp would put 5 warps on one SM sub-partition and cap every
+// thread at 96 registers (16384 / 5 / 32, rounded down to 8).  A full producer WARPGROUP instead lets the kernel
+// re-balance with setmaxnreg: the 4 producer warps drop to 24 registers, the 16 consumers rise to 120.
+template <int WARPS> constexpr int eddy_producer_warps() { return WARPS == 16 ? 4 : 1; }
+
 template <int BM, int NJ, int WARPS, bool TWO>
-__global__ void __launch_bounds__((WARPS + 1) * 32, 1)
+__global__ void __launch_bounds__((WARPS + eddy_producer_warps<WARPS>()) * 32, 1)
 k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     constexpr int MT = BM / 8;          // m8-tiles per CTA
+    constexpr int PW = eddy_producer_warps<WARPS>();
     constexpr int NW2 = WARPS / MT;     // warps per m-tile group (2, 4, 8 or 16)
     // GEMM1: a group owns 8 units (4 fields x 2 n8-tiles of the 16-column chunk) of its m-tile
     //   NW2 = 2: 2 fields x 2 n-tiles per warp;  NW2 = 4: 2 fields x 1 n-tile (fewest LDS per DMMA once two chunks
@@ -131,9 +137,10 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     }
     __syncthreads();
 
-    if (warp == WARPS) {
+    if (warp >= WARPS) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        if constexpr (PW == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");
+        if (warp == WARPS && lane == 0) {
             for (int f = 0; f < 4; f++) tma_prefetch_desc(&maps.x[f]);
             tma_prefetch_desc(&maps.q);
             for (int i = 0; i < nloc; i++) {
@@ -152,11 +159,18 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     }
 
     // ------------------------------ consumers ------------------------------
+    if constexpr (PW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;\n");
     const int g = lane >> 2, t = lane & 3;
     const int tid = threadIdx.x;   // 0 .. WARPS*32-1
     // spectral coefficients of the 4 fields for this CTA's rows -> Cs[f][r][LS]
+    // GEMM1 maps DMMA row g of an m-tile to physical tile row rho(g) = (g >> 1) | ((g & 1) << 2): the eight lanes of
+    // a quarter-warp (g = 2q, 2q+1) then touch rows q and q+4, whose 128-B-swizzled 16-byte chunks fall in opposite
+    // halves of the row, so the LDS.128 / STS.128 of the eddy phase take the minimum 4 wavefronts (the natural
+    // mapping pairs rows 2q, 2q+1 on the same four chunks: 8 wavefronts, ncu r01_prof_eddy3).  Cs slot s therefore
+    // holds the coefficients of row (s & ~7) + rho(s & 7).  GEMM2 reads the E tiles with the natural row mapping.
     for (int fr = warp; fr < 4 * BM; fr += WARPS) {
-        const int f = fr / BM, r = fr % BM;
+        const int f = fr / BM, rs = fr % BM;
+        const int r = (rs & ~7) | ((rs & 7) >> 1) | ((rs & 1) << 2);
         const int row = row0 + r;
         const double* src = p.coef4 + ((size_t)f * p.rows + row) * lpad;
         double* dst = Cs + (size_t)fr * p.ls;
@@ -189,9 +203,10 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     const int j_cnt = ((wq + 1) * p.nt) / NW2 - j_begin;      // NJ or NJ-1 (NJ = ceil(nt / NW2))
 
     // theta scale for this thread's row (field 2 only)
+    const int g1 = (g >> 1) | ((g & 1) << 2);   // rho(g): physical row of this thread's GEMM1 accumulators
     double tscale = 1.0;
     {
-        const int row = row0 + mi * 8 + g;
+        const int row = row0 + mi * 8 + g1;
         if (p.lev_scale != nullptr && row < p.rows) tscale = p.lev_scale[row % p.nlev];
     }
 
@@ -261,7 +276,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
         for (int c = 0; c < NCH; c++)
 #pragma unroll
             for (int nn = 0; nn < NN1; nn++) {
-                const int row = mi * 8 + g;
+                const int row = mi * 8 + g1;
                 const int col = (jn1 + nn) * 8 + 2 * t;
                 const uint32_t off = swz_off(row, col);
                 double e0[NF1], e1[NF1];
@@ -340,7 +355,7 @@ static int launch_eddy_2(const EddyMaps& maps, const EddyParams& p, int smem, cu
     cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ, WARPS, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (p.rows + BM - 1) / BM;
-    k_eddy<BM, NJ, WARPS, TWO><<<ntiles * p.nsplit, (WARPS + 1) * 32, smem, stream>>>(maps, p);
+    k_eddy<BM, NJ, WARPS, TWO><<<ntiles * p.nsplit, (WARPS + eddy_producer_warps<WARPS>()) * 32, smem, stream>>>(maps, p);
     return (int)cudaGetLastError();
 }
 

@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(256) k_epi_scan(const EpiDev e) {
     extern __shared__ double sm[];
     double* sv = sm;                                   // [lev][32]
     double* so = sm + (size_t)SCAN_MAXLEV * SCAN_LATS; // [lev][32]
-    const int t = blockIdx.y;
-    const int lat0 = blockIdx.x * SCAN_LATS;
+    const int nlb = (e.nlat + SCAN_LATS - 1) / SCAN_LATS;   // grid.x = nt * nlb (grid.y would cap nt at 65535)
+    const int t = blockIdx.x / nlb;
+    const int lat0 = (blockIdx.x % nlb) * SCAN_LATS;
     const int nl = min(SCAN_LATS, e.nlat - lat0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* vb = ZM(Z_VB) + (size_t)t * e.nlev * e.ld + lat0;
@@ -285,8 +286,9 @@ int launch_tem_epilogue(const EpilogueArgs& wrap, cudaStream_t stream) {
     k_epi_a<<<blocks, 256, 0, stream>>>(e);
     {
         const int smem = 2 * SCAN_MAXLEV * SCAN_LATS * (int)sizeof(double);
-        cudaFuncSetAttribute(k_epi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device
-        dim3 grid((a.nlat + SCAN_LATS - 1) / SCAN_LATS, a.nt);
+        const cudaError_t ea = cudaFuncSetAttribute(k_epi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device
+        if (ea != cudaSuccess) return (int)ea;
+        const unsigned grid = (unsigned)(((a.nlat + SCAN_LATS - 1) / SCAN_LATS) * (size_t)a.nt);
         k_epi_scan<<<grid, 256, smem, stream>>>(e);
     }
     k_epi_b<<<blocks, 256, 0, stream>>>(e);

@@ -5,6 +5,7 @@ libtemd kernel launch.  No CPU fallback: constructing an Engine without the libr
 CUDA device raises.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -54,6 +55,7 @@ class Engine:
         self.lpad = self.lib.temd_plan_lpad(self._plan)
         self.built = False
         self.sanity = None
+        self.lock = threading.RLock()   # serialises callers that share this (cached) engine's per-call state
 
     def __del__(self):
         try:
@@ -165,13 +167,36 @@ class Engine:
         _lib.check(rc, 'temd_multiply')
         return out[:, :n]
 
-    def check_finite(self, t, what='input'):
-        rc = self.lib.temd_check_finite(_ptr(t), t.numel(), self.stream)
+    def scan_nonfinite(self, t):
+        """'nan' if the device tensor holds a NaN, 'inf' if it holds infinities but no NaN, else None."""
+        t = t if t.dtype == torch.float64 and t.is_contiguous() else t.to(torch.float64).contiguous()
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_check_finite(_ptr(t), t.numel(), self.stream)
         if rc == -2:
+            return 'nan'
+        if rc == -6:
+            return 'inf'
+        _lib.check(rc, 'temd_check_finite')
+        return None
+
+    def check_finite(self, t, what='input', classify=None):
+        """NaN screen of sph_zonal_mean.py:219-221.  `t` is normally the small coefficient block (non-finite inputs
+        propagate into it); `classify()` is then called on failure only and looks at the inputs themselves, because an
+        infinity in a field also turns into NaN coefficients while the reference screens NaN only."""
+        kind = self.scan_nonfinite(t)
+        if kind is None:
+            return
+        if classify is not None:
+            kind = classify()
+        if kind == 'nan':
             # same failure the reference raises at sph_zonal_mean.py:219-221
             raise RuntimeError('Variable {} has nans! Spectral zonal averager cannot handle nans; '
                                'please replace or remove them'.format(what))
-        _lib.check(rc, 'temd_check_finite')
+        if kind == 'inf':
+            # the reference lets infinities through and returns inf/nan results; fail loudly instead
+            raise RuntimeError('Variable {} has infinite values (no nans); the spectral zonal mean of such a field '
+                               'is undefined'.format(what))
+        raise RuntimeError('Variable {}: all inputs are finite but the projection overflowed'.format(what))
 
     def eddy_flux_project(self, u, v, t, w, coef4, lev_scale, nlev):
         for x in (u, v, t, w):

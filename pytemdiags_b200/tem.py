@@ -28,6 +28,18 @@ _DERIVED = ('dub_dp', 'dthetab_dp', 'ubcoslat', 'dubcoslat_dlat', 'psi', 'psicos
             'dpsi_dp', 'int_vbdp')
 
 
+# pinned host staging buffers for pageable inputs: (device, slot) -> [pinned uint8 tensor, last-DMA event]
+_HOST_STAGING = {}
+
+
+def release_host_staging():
+    """Free the page-locked staging buffers kept for pageable host inputs (they are re-created on demand)."""
+    for ent in _HOST_STAGING.values():
+        if ent[1] is not None:
+            ent[1].synchronize()
+    _HOST_STAGING.clear()
+
+
 def _is_1d_of_len(x, n):
     try:
         r = ar.raw(x)
@@ -369,17 +381,22 @@ class TEMDiagnostics:
             self._whole[v] = d
 
     def _stage_pinned(self, r, slot):
-        '''Pageable host tensor -> pinned staging tensor (cached on the engine, one per (buffer set, field)) by a
-        multi-threaded memcpy in libtemd, so the following H2D copy is an asynchronous DMA.'''
+        '''Pageable host tensor -> pinned staging tensor (process-wide cache, one per (device, buffer set, field),
+        capped by TEMD_STAGING_MAX_BYTES and freed by `release_host_staging()`) by a multi-threaded memcpy in libtemd,
+        so the following H2D copy is an asynchronous DMA.'''
         import ctypes as C
         import os
         eng = self.ZM._engine
-        cache = eng.__dict__.setdefault('_pinned_stage', {})
         nbytes = r.numel() * r.element_size()
-        ent = cache.get(slot)
+        key = (str(eng.device), slot)
+        ent = _HOST_STAGING.get(key)
         if ent is None or ent[0].numel() < nbytes:
+            _HOST_STAGING.pop(key, None)
+            cap = int(os.environ.get('TEMD_STAGING_MAX_BYTES', 8 << 30))
+            if sum(e[0].numel() for e in _HOST_STAGING.values()) + nbytes > cap:
+                release_host_staging()
             ent = [torch.empty(nbytes, dtype=torch.uint8).pin_memory(), None]
-            cache[slot] = ent
+            _HOST_STAGING[key] = ent
         if ent[1] is not None:
             ent[1].synchronize()          # the previous DMA out of this staging buffer must have finished
         rc = eng.lib.temd_host_copy(C.c_void_p(ent[0].data_ptr()), C.c_void_p(r.data_ptr()), nbytes,
@@ -400,6 +417,10 @@ class TEMDiagnostics:
         project / eddy-flux kernels on the compute stream, slab i+1 is copied host->device (or
         re-laid-out) on a second stream.'''
         eng = self.ZM._engine
+        with eng.lock:      # cached engines are shared: per-call state (epilogue planes, staging) is not re-entrant
+            self._compute_all_locked(eng)
+
+    def _compute_all_locked(self, eng):
         dev = eng.device
         K, T, N = self.NLEV, self.NT, self.NCOL
         # theta = T (p0/p)^k per level (tem_diagnostics.py:498), in the input's level order
@@ -503,9 +524,21 @@ class TEMDiagnostics:
                     consumed[i % 2] = ev_
                 main.wait_stream(side)
                 self._whole = {}
-        eng.check_finite(coef, 'ua/va/ta/wap')       # sph_zonal_mean.py:219-221
+        def classify(vs):
+            # failure path only: look at the inputs themselves (a time step at a time) to tell NaN from infinity
+            def run():
+                found = None
+                for v in vs:
+                    for t0 in range(T):
+                        k_ = eng.scan_nonfinite(self._slab(v, t0, t0 + 1, dev))
+                        if k_ == 'nan':
+                            return 'nan'
+                        found = found or k_
+                return found
+            return run
+        eng.check_finite(coef, 'ua/va/ta/wap', classify(names[:4]))       # sph_zonal_mean.py:219-221
         if ntr:
-            eng.check_finite(coefq, 'q')
+            eng.check_finite(coefq, 'q', classify(names[4:]))
         self._coef_in = coef           # coefficient rows in the INPUT's level order (for the native-grid properties)
         self._coefq_in = coefq
         self._lev_scale = lev_scale

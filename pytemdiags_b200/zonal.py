@@ -4,6 +4,8 @@ Same constructor arguments, methods, attributes and error behaviour; the matrice
 from / written to `maps/*.nc` (the basis is regenerated on the GPU in milliseconds), so the
 cache-related arguments are accepted and ignored.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -13,7 +15,7 @@ from .engine import Engine
 # Engines (plan + orthonormalised basis in HBM) are kept per (grid, output grid, L, device), the device-memory
 # analogue of the reference's on-disk `maps/Y0_*.nc` cache (sph_zonal_mean.py:165-177,330-345).
 _ENGINE_CACHE = {}
-_ENGINE_CACHE_MAX = 2
+_ENGINE_CACHE_MAX = int(os.environ.get('TEMD_ENGINE_CACHE', '4'))   # plans kept (2.6 GB of basis each at config 3)
 
 
 def _cached_engine(lat, lat_out, L, device, overwrite=False, weights=None):
@@ -154,12 +156,13 @@ class sph_zonal_averager:
             buf = torch.zeros((x2.shape[0], ld), dtype=torch.float64, device=eng.device)
             buf[:, :self.N] = x2
             x2 = buf[:, :self.N]
-        coef = eng.project([x2])
-        eng.check_finite(coef, name)
-        if native:
-            res = eng.synth_native(coef[0])                # (DD, N)
-        else:
-            res = eng.synth_out(coef)[0]                   # (DD, M)
+        with eng.lock:
+            coef = eng.project([x2])
+            eng.check_finite(coef, name, lambda: eng.scan_nonfinite(x2))
+            if native:
+                res = eng.synth_native(coef[0])                # (DD, N)
+            else:
+                res = eng.synth_out(coef)[0]                   # (DD, M)
         NN = res.shape[1]
         if ncol_last and kind != 'dataarray':
             res = res.reshape(tuple(rest) + (NN,))

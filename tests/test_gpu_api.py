@@ -144,6 +144,18 @@ def test_error_behaviour():
     x = np.zeros(lat.shape[0]); x[5] = np.nan
     with pytest.raises(RuntimeError, match='nans'):
         ZM.sph_zonal_mean(x)
+    # the reference screens NaN only (sph_zonal_mean.py:219): an infinity is reported as what it is, not as "nans"
+    x[5] = np.inf
+    with pytest.raises(RuntimeError, match='infinite') as ei:
+        ZM.sph_zonal_mean(x)
+    assert 'has nans' not in str(ei.value)
+    badi = f['wap'].copy()
+    badi[0, 1, 7] = -np.inf
+    with pytest.raises(RuntimeError, match='infinite'):
+        TEMDiagnostics(f['ua'], f['va'], f['ta'], badi, plev, lat, L=10, dims=('time', 'lev', 'ncol'), debug_level=0)
+    badi[1, 0, 0] = np.nan          # NaN wins over infinity, as in the reference
+    with pytest.raises(RuntimeError, match='nans'):
+        TEMDiagnostics(f['ua'], f['va'], f['ta'], badi, plev, lat, L=10, dims=('time', 'lev', 'ncol'), debug_level=0)
 
 
 def test_zonal_averager_weights_path():

@@ -1,24 +1,47 @@
-"""torchrun --nproc-per-node N tools/sharded_check.py : ShardedTEM over N real GPUs (NCCL) vs the unsharded result."""
-import os, sys
+"""torchrun --nproc-per-node N tools/sharded_check.py : ShardedTEM over N real GPUs vs the unsharded result.
+
+Checks, bit for bit: `gather_all()` (ONE all-gather for the ten public outputs + the tracer diagnostics) through
+torch.distributed/NCCL and through libtemd's own NCCL call (`TemdComm` -> temd_allgather_outputs), with uneven time
+slabs (T = 7) and, when N > 7 or with --empty, ranks that own an EMPTY slab."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
+import numpy as np
+import torch
+import torch.distributed as dist
+
 from pytemdiags_b200 import TEMDiagnostics, synthetic as syn
-from pytemdiags_b200.distributed import ShardedTEM, shard_bounds
+from pytemdiags_b200.distributed import PUBLIC_OUTPUTS, TRACER_PUBLIC, ShardedTEM, TemdComm, shard_bounds
+
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
-dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-lat, lon = syn.pg2_grid(12); K, T, L = 9, 7, 40          # T = 7 is not divisible by 2/4/8: uneven slabs
-plev = syn.default_plev(K)
-f = syn.synth_fields(lat, lon, plev, T, seed=33)
-a, b = shard_bounds(T, world)[rank]
-sh = ShardedTEM(f['ua'][a:b], f['va'][a:b], f['ta'][a:b], f['wap'][a:b], plev, lat, T=T, L=L, dims=('time', 'lev', 'ncol'),
-                debug_level=0, device='cuda:%d' % local) if b > a else None
-full = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=L, dims=('time', 'lev', 'ncol'), debug_level=0,
-                      device='cuda:%d' % local)
+dev = 'cuda:%d' % local
+dist.init_process_group('nccl', device_id=torch.device(dev))
+lat, lon = syn.pg2_grid(12)
+K, L = 9, 40
 ok = True
-for n in ('vtem', 'epfy', 'epdiv', 'psitem', 'utendwtem'):
-    got = sh.gather(n).cpu().numpy()
-    ok &= bool(np.array_equal(got, getattr(full, n)()))
-print('rank %d/%d slab [%d,%d) sharded == unsharded: %s' % (rank, world, a, b, ok), flush=True)
+for T in ((7, 1) if '--empty' in sys.argv or world > 7 else (7,)):     # 7: uneven slabs; 1: empty slabs on ranks > 0
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=33, fields=('ua', 'va', 'ta', 'wap', 'q'))
+    a, b = shard_bounds(T, world)[rank]
+    kw = dict(L=L, dims=('time', 'lev', 'ncol'), debug_level=0, device=dev)
+    full = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, q=f['q'], **kw)
+    ids = [TemdComm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = TemdComm(world, rank, ids[0], dev)
+    for transport, c in (('torch.distributed', None), ('libtemd nccl', comm)):
+        sh = ShardedTEM(f['ua'][a:b], f['va'][a:b], f['ta'][a:b], f['wap'][a:b], plev, lat, q=f['q'][a:b], T=T, comm=c, **kw)
+        out = sh.gather_all()
+        good = sh.T == T
+        for n in PUBLIC_OUTPUTS:
+            good &= bool(np.array_equal(out[n].cpu().numpy(), getattr(full, n)()))
+        for n in TRACER_PUBLIC:
+            good &= bool(np.array_equal(out[n][0].cpu().numpy(), getattr(full, n)(0)))
+        good &= bool(np.array_equal(sh.gather('psitem').cpu().numpy(), full.psitem()))
+        print('rank %d/%d T=%d slab [%d,%d) %s: sharded == unsharded: %s' % (rank, world, T, a, b, transport, good), flush=True)
+        ok &= good
+    comm.close()
+dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
