@@ -86,7 +86,8 @@ int temd_eddy_flux_project(temd_plan* plan, const double* u, const double* v, co
 /* _compute_derivatives + the ten diagnostics methods (tem_diagnostics.py:574-797; tem_util.py:57-243).
  * zm: 7 zonal-mean arrays [nt][nlev][M] in the order ub, vb, thetab, wapb, upvpb, upwappb, vptpb.
  * gp/gl: np.gradient coefficient triplets (a,b,c) per level [3][nlev] / per latitude [3][M].
- * out: TEMD_NOUT arrays [nt][nlev][M] in the order of TEMD_OUT_* below (+2 scratch planes). */
+ * out: TEMD_NOUT arrays [nt][nlev][M] in the order of TEMD_OUT_* below (+2 planes kept for ABI compatibility with
+ * v100, which staged F_phi cos(phi) / F_p there; no longer written). */
 typedef struct temd_epilogue_args {
     int nt, nlev, nlat;
     size_t ld;              /* leading dimension (>= nlat) of every [nt*nlev][ld] plane */
@@ -100,7 +101,7 @@ typedef struct temd_epilogue_args {
     const double* coslat;   /* [nlat] */
     const double* f;        /* [nlat] Coriolis parameter */
     double p0, a, H, g0, pi;
-    double* out;            /* [TEMD_NOUT + 2][nt*nlev][ld]; the last two planes are scratch */
+    double* out;            /* [TEMD_NOUT + 2][nt*nlev][ld]; the last two planes are unused (v100 scratch) */
 } temd_epilogue_args;
 
 enum {
@@ -116,7 +117,7 @@ int temd_tem_epilogue(temd_plan* plan, const temd_epilogue_args* args, void* str
  * qtendvtem/qtendwtem :801-991) for ONE tracer.  zmq: [3][nt*nlev][ld] = qb, qpvpb, qpwappb (obtained with
  * temd_project on q and temd_eddy_flux_project on (q, v, T, omega), whose first two products are then
  * q'v' and q'omega').  psi / vtem / omegatem: planes written by temd_tem_epilogue.
- * out: [TEMD_NTROUT + 2][nt*nlev][ld], last two planes scratch. */
+ * out: [TEMD_NTROUT + 2][nt*nlev][ld], last two planes unused (v100 scratch). */
 typedef struct temd_tracer_args {
     int nt, nlev, nlat;
     size_t ld;
@@ -151,6 +152,41 @@ int temd_check_finite(const double* data, size_t n, void* stream);
  * pinned buffers ahead of the asynchronous host->device copy.  No reference counterpart (the reference never leaves
  * the host). */
 int temd_host_copy(void* dst_host, const void* src_host, size_t bytes, int nthreads);
+
+/* ---- Structure-exploiting fast path, opt-in -------------------------------------------------
+ * Rows of Y0 depend on latitude only (sph_zonal_mean.py:361-363): columns with the same x = sin(lat) form a group
+ * (a raveled lat-lon grid, tem_util.py:331, has NLAT groups of NLON columns).  The plan is created on the U unique
+ * nodes and factorised with temd_basis_build_dedup (basis rows weighted by sqrt(multiplicity): same Gram matrix, same
+ * coefficients as the dense path).  Group description, all device pointers: goff[U+1] offsets into the group-sorted
+ * column list, perm[ncol] sorted position -> column (NULL when every group is a contiguous column range),
+ * gid[ncol] column -> group, rsq[U] = 1/sqrt(multiplicity). */
+int temd_basis_build_dedup(temd_plan* plan, const double* x_unique, const double* x_out, const double* mult,
+                           double* sanity_host, void* stream);
+
+/* One pass over the fields (HBM bound).  with_products = 0: out[f][row][u] = (sum_{i in u} fields[f][row][i]) * rsq[u]
+ * for f < nfields <= 4 - the input of temd_project on the unique grid.  with_products = 1 (fields = u, v, T, omega;
+ * lev_scale/scale_field as in temd_project turn T into theta): TEMD_GS_NPLANES planes [row][ld_out]:
+ *   0-3 a0_f (first member of the group), 4-7 s_f = sum (x_f - a0_f), 8-10 sum (x_a - a0_a)(x_b - a0_b) for
+ *   (a,b) = (u,v), (u,omega), (v,theta), 11-14 the weighted sums of with_products = 0.
+ * max_count / min_count: largest / smallest multiplicity (selects the warp-per-group and thread-per-group kernels). */
+#define TEMD_GS_NPLANES 15
+int temd_group_sums(const double* const* fields_host, int nfields, int rows, size_t ld, const int* perm,
+                    const int* goff, int ngroups, int max_count, int min_count, const double* rsq,
+                    const double* lev_scale, int scale_field, int nlev, int with_products, double* out,
+                    size_t ld_out, void* stream);
+
+/* Eddy-flux group sums about the spectral zonal means (tem_diagnostics.py:517-529,547-555 without materialising
+ * eddies): means_w [4][rows][ld_m] = temd_synth_native of the four coefficient blocks on the unique grid
+ * (= sqrt(n_u) * zonal mean); out [3][rows][ld_out] = rsq[u] * sum_{i in u} a'_i b'_i for u'v', u'omega', v'theta',
+ * ready for temd_project on the unique grid. */
+int temd_dedup_flux(const double* gsums, size_t ld_gs, const double* means_w, size_t ld_m, const int* goff,
+                    const double* rsq, int rows, int ngroups, double* out, size_t ld_out, void* stream);
+
+/* out[row][i] = alpha * lev_scale[row % nlev] * x[row][i] + beta * rsq[gid[i]] * means_w[row][gid[i]]
+ * (x NULL: expanded native zonal mean, sph_zonal_mean.py:285-290; alpha 1, beta -1: eddy field). rsq NULL = 1. */
+int temd_dedup_expand(const double* x, size_t ld_x, const double* lev_scale, int nlev, const double* means_w,
+                      size_t ld_m, const int* gid, const double* rsq, double alpha, double beta, double* out,
+                      size_t ld_out, int rows, int ncol, void* stream);
 
 /* Multi-GPU: time steps never interact (sph_zonal_mean.py:244-251, tem_util.py:154,192,232), so each
  * process owns a time slab and the only exchange is ONE all-gather of the stacked output planes at the end.

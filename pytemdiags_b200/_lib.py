@@ -14,6 +14,7 @@ SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
     'temd_basis_build', 'temd_basis_build_weighted', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
     'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_host_copy', 'temd_synth_fields',
+    'temd_basis_build_dedup', 'temd_group_sums', 'temd_dedup_flux', 'temd_dedup_expand',
     'temd_comm_unique_id', 'temd_comm_init', 'temd_comm_destroy', 'temd_allgather_outputs',
 )
 
@@ -33,6 +34,9 @@ class EpilogueArgs(C.Structure):
                 ('p0', C.c_double), ('a', C.c_double), ('H', C.c_double), ('g0', C.c_double), ('pi', C.c_double),
                 ('out', C.c_void_p)]
 
+
+GS_NPLANES = 15          # TEMD_GS_NPLANES
+GS_A0, GS_S, GS_P, GS_SW = 0, 4, 8, 11
 
 TRACER_OUTPUTS = ('dqb_dp', 'qbcoslat', 'dqbcoslat_dlat', 'etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem')
 
@@ -54,6 +58,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if 'TEMD_LIB' not in os.environ:
+        # a library older than its sources is a stale build (e.g. an edit without `python -m pytemdiags_b200.build`):
+        # rebuild rather than run yesterday's kernels.  nvcc is part of the image; failure to build is loud.
+        from . import build as _build
+        try:
+            stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < _build._newest_source_mtime()
+        except OSError:
+            stale = False
+        if stale and os.environ.get('TEMD_NO_AUTOBUILD', '0') in ('', '0'):
+            _build.build(force=True)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError('libtemd.so not found at %s: run `python -m pytemdiags_b200.build` '
                            '(there is no CPU fallback)' % LIB_PATH)
@@ -78,6 +92,10 @@ def load():
     lib.temd_check_finite.argtypes = [vp, sz, vp]
     lib.temd_host_copy.argtypes = [vp, vp, sz, i]
     lib.temd_synth_fields.argtypes = [vp, i, i, i, i, i, i, sz, vp, vp, vp, vp]
+    lib.temd_basis_build_dedup.argtypes = [vp, vp, vp, vp, C.POINTER(d), vp]
+    lib.temd_group_sums.argtypes = [C.POINTER(vp), i, i, sz, vp, vp, i, i, i, vp, vp, i, i, i, vp, sz, vp]
+    lib.temd_dedup_flux.argtypes = [vp, sz, vp, sz, vp, vp, i, i, vp, sz, vp]
+    lib.temd_dedup_expand.argtypes = [vp, sz, vp, i, vp, sz, vp, vp, d, d, vp, sz, i, i, vp]
     lib.temd_comm_unique_id.argtypes = [C.c_char_p]
     lib.temd_comm_init.argtypes = [i, i, i, C.c_char_p, C.POINTER(vp)]
     lib.temd_comm_destroy.argtypes = [vp]

@@ -150,6 +150,14 @@ __global__ void k_scale_cols(const double* __restrict__ in, const double* __rest
     out[(size_t)l * ld + i] = (i < (size_t)n) ? in[(size_t)l * ld + i] * w[i] : 0.0;
 }
 
+// in[l][n] *= sqrt(m[n])   (weighted unique grid of the de-duplicated path)
+__global__ void k_scale_cols_sqrt(double* __restrict__ q, const double* __restrict__ m, int rows, int n, size_t ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (i >= (size_t)n || l >= rows) return;
+    q[(size_t)l * ld + i] *= sqrt(m[i]);
+}
+
 // out[i][j] = in[j][i]; in is [rows_in][ld_in], out is [cols_in][ld_out]  (dense exports only)
 __global__ void k_transpose(const double* __restrict__ in, int rows_in, int cols_in, size_t ld_in,
                             double* __restrict__ out, size_t ld_out) {
@@ -204,7 +212,7 @@ static int ensure_work(temd_plan* p, cudaStream_t stream, size_t doubles, double
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
-extern "C" int temd_version(void) { return 100; }
+extern "C" int temd_version(void) { return 101; }
 extern "C" const char* temd_last_error(void) { return g_err; }
 
 extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_plan** out) {
@@ -273,7 +281,11 @@ static int gram_of(temd_plan* p, const double* basis, cudaStream_t st) {
     return launch_project(xs, 1, p->Lp, p->N, p->ld_q, basis, p->lpad, p->ld_q, p->gram, work, nsplit, nullptr, -1, 1, st);
 }
 
-extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_out, double* sanity_host, void* stream) {
+// `mult` (nullable): multiplicity of every node.  The raw basis rows are then scaled by sqrt(mult) before the
+// factorisation (weighted unique grid of the de-duplicated fast path, temd_dedup.cu): its Gram matrix is the Gram
+// matrix of the full grid in which node u appears mult[u] times.
+static int basis_build_impl(temd_plan* p, const double* x, const double* x_out, const double* mult, double* sanity_host,
+                            void* stream) {
     if (p == nullptr || x == nullptr || x_out == nullptr) return temd_set_error(-1, "basis_build: null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TEMD_ON_DEVICE(p->dev);
@@ -295,6 +307,11 @@ extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_o
     // K1: raw basis (transposed) on both grids
     if ((rc = launch_basis(p->x, p->N, p->L, p->rec_a, p->rec_b, p->qt_alt, p->ld_q, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
     if ((rc = launch_basis(p->x_out, p->M, p->L, p->rec_a, p->rec_b, p->qpt_alt, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis kernel launch failed");
+    if (mult != nullptr) {
+        dim3 grid((unsigned)((p->ld_q + 255) / 256), p->lpad);
+        k_scale_cols_sqrt<<<grid, 256, 0, st>>>(p->qt_alt, mult, p->lpad, p->N, p->ld_q);
+        TEMD_CUDA(cudaGetLastError());
+    }
     // CholeskyQR2: G = Y^T Y = L L^T, Y <- Y L^-T, twice (the second pass removes the cond(Y0)^2 eps loss of
     // orthogonality of the first); L^-1 accumulates as L2^-1 L1^-1.  If the first factorisation breaks down
     // (cond(Y0) >~ 3e6), a shifted first pass (G + s I, s = 11 (N Lp + Lp(Lp+1)) eps trace(G), "shifted
@@ -349,6 +366,16 @@ extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_o
     p->built = true;
     p->weighted = false;
     return 0;
+}
+
+extern "C" int temd_basis_build(temd_plan* p, const double* x, const double* x_out, double* sanity_host, void* stream) {
+    return basis_build_impl(p, x, x_out, nullptr, sanity_host, stream);
+}
+
+extern "C" int temd_basis_build_dedup(temd_plan* p, const double* x_unique, const double* x_out, const double* mult,
+                                      double* sanity_host, void* stream) {
+    if (mult == nullptr) return temd_set_error(-1, "basis_build_dedup: null multiplicities");
+    return basis_build_impl(p, x_unique, x_out, mult, sanity_host, stream);
 }
 
 extern "C" int temd_basis_build_weighted(temd_plan* p, const double* x, const double* x_out, const double* w, void* stream) {
@@ -560,6 +587,55 @@ extern "C" int temd_tracer_epilogue(temd_plan* p, const temd_tracer_args* args, 
     TEMD_ON_DEVICE(p->dev);
     int rc = launch_tracer_epilogue(*args, reinterpret_cast<cudaStream_t>(stream));
     if (rc) return temd_set_error(rc, "tracer_epilogue: kernel launch failed");
+    return 0;
+}
+
+namespace temd {
+int launch_group_sums(const double* const* x, int nfields, int rows, size_t ld, const int* perm, const int* goff,
+                      int ngroups, int max_count, int min_count, const double* rsq, const double* lev_scale,
+                      int scale_field, int nlev, int with_products, double* out, size_t ld_out, cudaStream_t stream);
+int launch_dedup_flux(const double* gs, size_t ld_gs, const double* mw, size_t ld_m, const int* goff, const double* rsq,
+                      int rows, int ngroups, double* out, size_t ld_o, cudaStream_t stream);
+int launch_dedup_expand(const double* x, size_t ld_x, const double* scale, int nlev, const double* mw, size_t ld_m,
+                        const int* gid, const double* rsq, double alpha, double beta, double* out, size_t ld_out, int rows,
+                        int n, cudaStream_t stream);
+}
+
+extern "C" int temd_group_sums(const double* const* fields_host, int nfields, int rows, size_t ld, const int* perm,
+                               const int* goff, int ngroups, int max_count, int min_count, const double* rsq,
+                               const double* lev_scale, int scale_field, int nlev, int with_products, double* out,
+                               size_t ld_out, void* stream) {
+    if (!fields_host || !goff || !rsq || !out || nfields < 1 || nfields > 4 || rows < 1 || ngroups < 1 ||
+        ld_out < (size_t)ngroups || min_count < 1 || max_count < min_count)
+        return temd_set_error(-1, "group_sums: bad arguments");
+    if (with_products && nfields != 4) return temd_set_error(-1, "group_sums: the flux sums need the four fields u, v, T, omega");
+    for (int f = 0; f < nfields; f++) if (!fields_host[f]) return temd_set_error(-1, "group_sums: null field");
+    const int rc = launch_group_sums(fields_host, nfields, rows, ld, perm, goff, ngroups, max_count, min_count, rsq, lev_scale,
+                                     lev_scale ? scale_field : -1, nlev, with_products, out, ld_out,
+                                     reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return temd_set_error(rc, "group_sums: kernel launch failed");
+    return 0;
+}
+
+extern "C" int temd_dedup_flux(const double* gsums, size_t ld_gs, const double* means_w, size_t ld_m, const int* goff,
+                               const double* rsq, int rows, int ngroups, double* out, size_t ld_out, void* stream) {
+    if (!gsums || !means_w || !goff || !rsq || !out || rows < 1 || ngroups < 1 || ld_gs < (size_t)ngroups ||
+        ld_m < (size_t)ngroups || ld_out < (size_t)ngroups)
+        return temd_set_error(-1, "dedup_flux: bad arguments");
+    const int rc = launch_dedup_flux(gsums, ld_gs, means_w, ld_m, goff, rsq, rows, ngroups, out, ld_out,
+                                     reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return temd_set_error(rc, "dedup_flux: kernel launch failed");
+    return 0;
+}
+
+extern "C" int temd_dedup_expand(const double* x, size_t ld_x, const double* lev_scale, int nlev, const double* means_w,
+                                 size_t ld_m, const int* gid, const double* rsq, double alpha, double beta, double* out,
+                                 size_t ld_out, int rows, int ncol, void* stream) {
+    if (!means_w || !gid || !out || rows < 1 || ncol < 1 || ld_out < (size_t)ncol || (x && ld_x < (size_t)ncol))
+        return temd_set_error(-1, "dedup_expand: bad arguments");
+    const int rc = launch_dedup_expand(x, ld_x, lev_scale, nlev, means_w, ld_m, gid, rsq, alpha, beta, out, ld_out, rows, ncol,
+                                       reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return temd_set_error(rc, "dedup_expand: kernel launch failed");
     return 0;
 }
 

@@ -93,7 +93,9 @@ __device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st,
 
 // Producer warps: with 16 consumer warps a single extra warp would put 5 warps on one SM sub-partition and cap every
 // thread at 96 registers (16384 / 5 / 32, rounded down to 8).  A full producer WARPGROUP instead lets the kernel
-// re-balance with setmaxnreg: the 4 producer warps drop to 24 registers, the 16 consumers rise to 120.
+// re-balance with setmaxnreg: the 4 producer warps drop to 24 registers, the 16 consumers rise to 112.  The CTA's
+// register pool is what it was launched with (640 threads x 96): 512 x 112 + 128 x 24 = 60416 <= 61440.  (A target
+// the pool cannot satisfy makes setmaxnreg.inc spin forever.)
 template <int WARPS> constexpr int eddy_producer_warps() { return WARPS == 16 ? 4 : 1; }
 
 template <int BM, int NJ, int WARPS, bool TWO>
@@ -159,7 +161,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     }
 
     // ------------------------------ consumers ------------------------------
-    if constexpr (PW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;\n");
+    if constexpr (PW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
     const int g = lane >> 2, t = lane & 3;
     const int tid = threadIdx.x;   // 0 .. WARPS*32-1
     // spectral coefficients of the 4 fields for this CTA's rows -> Cs[f][r][LS]

@@ -5,7 +5,11 @@
 // epdiv (:730-736), utendepfd (:753), utendvtem (:771-773), utendwtem (:790-791), and the helpers in
 // PyTEMDiags/tem_util.py: multiply_lat (:80), multiply_p (:117), lat_gradient (:154),
 // p_gradient (:192), p_integral (:230-232).  Arrays are [time][lev][lat] (lat contiguous, leading
-// dimension ld) and tiny (2.5 MB each at config 1): three L2-resident passes, HBM/L2-bound.
+// dimension ld) and tiny (2.5 MB each at config 1).  TWO launches: k_epi_1 (first derivatives, psi and the pressure
+// integral, one CTA per (time step, 32 latitudes) so that the scan along the level axis stays inside the CTA) and
+// k_epi_2 (everything that needs psi neighbours, and the EP-flux divergence, whose F_phi cos(phi) / F_p neighbours
+// are re-evaluated from the planes of k_epi_1 instead of being staged through scratch planes and a third pass).
+// The tracer epilogue is ONE launch (k_tr) with the same halo re-evaluation.  HBM/L2-bound.
 //
 // np.gradient semantics (edge_order=1): one-sided first differences at the two ends; interior is
 // a*f[i-1] + b*f[i] + c*f[i+1] with the non-uniform second-order coefficients, or
@@ -46,7 +50,6 @@ struct EpiDev {
 #define ZM(q) (e.zm + (size_t)(q) * e.plane)
 #define OUT(q) (e.out + (size_t)(q) * e.plane)
 enum { Z_UB = 0, Z_VB, Z_THETAB, Z_WAPB, Z_UPVPB, Z_UPWAPPB, Z_VPTPB };
-enum { S_FPHICOS = TEMD_NOUT, S_FP = TEMD_NOUT + 1 };
 
 __device__ __forceinline__ bool epi_index(const EpiDev& e, int& t, int& k, int& m, size_t& idx) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,10 +62,8 @@ __device__ __forceinline__ bool epi_index(const EpiDev& e, int& t, int& k, int& 
     return true;
 }
 
-// pass A: dub_dp, dthetab_dp, psi, ubcoslat, dubcoslat_dlat, psicoslat   (tem_diagnostics.py:579-592)
-__global__ void k_epi_a(const EpiDev e) {
-    int t, k, m; size_t idx;
-    if (!epi_index(e, t, k, m, idx)) return;
+// pass A for one point: dub_dp, dthetab_dp, psi, ubcoslat, dubcoslat_dlat, psicoslat   (tem_diagnostics.py:579-592)
+__device__ __forceinline__ void epi_point_a(const EpiDev& e, int k, int m, size_t idx) {
     const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
     const double* ub = ZM(Z_UB);
     const double* th = ZM(Z_THETAB);
@@ -81,23 +82,31 @@ __global__ void k_epi_a(const EpiDev e) {
     OUT(TEMD_OUT_PSICOSLAT)[idx] = psi * c0;                                          // :592
 }
 
-// int_vbdp (tem_util.py:230-232): cumulative trapezoid from the model top,
+// k_epi_1 = pass A + int_vbdp (tem_util.py:230-232): cumulative trapezoid from the model top,
 //   out[k] = sum_{j<=k} (p_j - p_{j-1}) (v_j + v_{j-1}) / 2,  out[0] = 0.
-// One CTA per (time step, 32 latitudes): the [nlev][32] slab is staged through shared memory with coalesced
-// loads, each warp scans 4 latitude columns along the level axis with warp shuffles (32 levels per pass, running
-// carry between passes), and the result leaves through shared memory again so the stores are coalesced too.
+// One CTA per (time step, 32 latitudes), grid.x = nt * ceil(nlat / 32) (nt in grid.x: no 65535 limit).  The CTA first
+// does pass A for its [nlev][32] tile (256-B row segments), then the scan: the [nlev][32] slab of vb is staged through
+// shared memory with coalesced loads, each warp scans 4 latitude columns along the level axis with warp shuffles
+// (32 levels per pass, running carry between passes), and the result leaves through shared memory again so the
+// stores are coalesced too.
 constexpr int SCAN_LATS = 32;
 constexpr int SCAN_MAXLEV = 160;     // levels staged per pass (shared memory: 2 x 160 x 32 x 8 B = 80 KB dynamic)
 
-__global__ void __launch_bounds__(256) k_epi_scan(const EpiDev e) {
+__global__ void __launch_bounds__(256) k_epi_1(const EpiDev e) {
     extern __shared__ double sm[];
     double* sv = sm;                                   // [lev][32]
     double* so = sm + (size_t)SCAN_MAXLEV * SCAN_LATS; // [lev][32]
-    const int nlb = (e.nlat + SCAN_LATS - 1) / SCAN_LATS;   // grid.x = nt * nlb (grid.y would cap nt at 65535)
+    const int nlb = (e.nlat + SCAN_LATS - 1) / SCAN_LATS;
     const int t = blockIdx.x / nlb;
     const int lat0 = (blockIdx.x % nlb) * SCAN_LATS;
     const int nl = min(SCAN_LATS, e.nlat - lat0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- pass A on this CTA's tile
+    for (int i = threadIdx.x; i < e.nlev * SCAN_LATS; i += blockDim.x) {
+        const int k = i / SCAN_LATS, ml = i % SCAN_LATS;
+        if (ml < nl) epi_point_a(e, k, lat0 + ml, ((size_t)t * e.nlev + k) * e.ld + lat0 + ml);
+    }
+    // ---- pressure integral
     const double* vb = ZM(Z_VB) + (size_t)t * e.nlev * e.ld + lat0;
     double* o = OUT(TEMD_OUT_INT_VBDP) + (size_t)t * e.nlev * e.ld + lat0;
     double carry[4] = {0.0, 0.0, 0.0, 0.0};            // running integral of this warp's 4 columns
@@ -140,8 +149,26 @@ __global__ void __launch_bounds__(256) k_epi_scan(const EpiDev e) {
     }
 }
 
-// pass B: everything that needs psi / psicoslat neighbours   (tem_diagnostics.py:594-597, 615-716, 763-797)
-__global__ void k_epi_b(const EpiDev e) {
+// F_phi cos(phi) and F_p of tem_diagnostics.py:730-733 at an arbitrary point, from the planes written by k_epi_1
+__device__ __forceinline__ double epi_epfy(const EpiDev& e, size_t idx, int m, double pk) {
+    return ((OUT(TEMD_OUT_DUB_DP)[idx] * OUT(TEMD_OUT_PSI)[idx] - ZM(Z_UPVPB)[idx]) * (e.a * e.coslat[m])) * (pk / e.p0);   // :691-692
+}
+__device__ __forceinline__ double epi_epfz(const EpiDev& e, size_t idx, int m) {
+    const double acos = e.a * e.coslat[m];
+    const double xz = e.f[m] - OUT(TEMD_OUT_DUBCOSLAT_DLAT)[idx] * (1.0 / acos);      // :709
+    return -e.H / e.p0 * ((xz * OUT(TEMD_OUT_PSI)[idx] - ZM(Z_UPWAPPB)[idx]) * acos); // :710
+}
+__device__ __forceinline__ double epi_fphicos(const EpiDev& e, size_t idx, int m, double pk) {
+    return (epi_epfy(e, idx, m, pk) * (e.p0 / pk)) * e.coslat[m];                     // :730, :733
+}
+__device__ __forceinline__ double epi_fp(const EpiDev& e, size_t idx, int m) {
+    return epi_epfz(e, idx, m) * -e.p0 / e.H;                                         // :731
+}
+
+// k_epi_2: everything that needs psi / psicoslat neighbours (tem_diagnostics.py:594-597, 615-716, 763-797) and the
+// EP-flux divergence (:734-736, 753), whose neighbour values of F_phi cos(phi) (lat +-1) and F_p (lev +-1) are
+// re-evaluated from the k_epi_1 planes.
+__global__ void k_epi_2(const EpiDev e) {
     int t, k, m; size_t idx;
     if (!epi_index(e, t, k, m, idx)) return;
     const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
@@ -152,15 +179,18 @@ __global__ void k_epi_b(const EpiDev e) {
     const double dpsi_dp = grad3(e.ap, k, psi_a[up], psi, psi_a[dn]);                 // :596
     const double dpsic_dlat = grad3(e.al, m, psic_a[lm], psic_a[idx], psic_a[lp]);    // :594
     const double c0 = e.coslat[m], pk = e.p[k];
-    const double acos = e.a * c0, iacos = 1.0 / (e.a * c0);
+    const double iacos = 1.0 / (e.a * c0);
     const double dub_dp = OUT(TEMD_OUT_DUB_DP)[idx];
     const double vtem = ZM(Z_VB)[idx] - dpsi_dp;                                      // :622
     const double omegatem = ZM(Z_WAPB)[idx] + dpsic_dlat * iacos;                     // :639
     const double wtem = omegatem * (-e.H / pk);                                       // :657
     const double psitem = 2 * e.pi * e.a / e.g0 * ((OUT(TEMD_OUT_INT_VBDP)[idx] - psi) * c0);   // :674
-    const double epfy = ((dub_dp * psi - ZM(Z_UPVPB)[idx]) * acos) * (pk / e.p0);     // :691-692
+    const double epfy = epi_epfy(e, idx, m, pk);
     const double xz = e.f[m] - OUT(TEMD_OUT_DUBCOSLAT_DLAT)[idx] * iacos;             // :709
-    const double epfz = -e.H / e.p0 * ((xz * psi - ZM(Z_UPWAPPB)[idx]) * acos);       // :710
+    const double epfz = epi_epfz(e, idx, m);
+    const int mm = (m > 0) ? m - 1 : m, mp = (m < e.nlat - 1) ? m + 1 : m;
+    const double epdiv = grad3(e.al, m, epi_fphicos(e, lm, mm, pk), (epfy * (e.p0 / pk)) * c0, epi_fphicos(e, lp, mp, pk)) * iacos
+                       + grad3(e.ap, k, epi_fp(e, up, m), epfz * -e.p0 / e.H, epi_fp(e, dn, m));               // :734-736
     OUT(TEMD_OUT_DPSI_DP)[idx] = dpsi_dp;
     OUT(TEMD_OUT_DPSICOSLAT_DLAT)[idx] = dpsic_dlat;
     OUT(TEMD_OUT_VTEM)[idx] = vtem;
@@ -171,22 +201,8 @@ __global__ void k_epi_b(const EpiDev e) {
     OUT(TEMD_OUT_EPFZ)[idx] = epfz;
     OUT(TEMD_OUT_UTENDVTEM)[idx] = vtem * xz;                                         // :771-773
     OUT(TEMD_OUT_UTENDWTEM)[idx] = -omegatem * dub_dp;                                // :790-791
-    OUT(S_FPHICOS)[idx] = (epfy * (e.p0 / pk)) * c0;                                  // :730, :733
-    OUT(S_FP)[idx] = epfz * -e.p0 / e.H;                                              // :731
-}
-
-// pass C: epdiv, utendepfd   (tem_diagnostics.py:734-736, 753)
-__global__ void k_epi_c(const EpiDev e) {
-    int t, k, m; size_t idx;
-    if (!epi_index(e, t, k, m, idx)) return;
-    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
-    const size_t lm = (m > 0) ? idx - 1 : idx, lp = (m < e.nlat - 1) ? idx + 1 : idx;
-    const double* fc = OUT(S_FPHICOS);
-    const double* fp = OUT(S_FP);
-    const double iacos = 1.0 / (e.a * e.coslat[m]);
-    const double epdiv = grad3(e.al, m, fc[lm], fc[idx], fc[lp]) * iacos + grad3(e.ap, k, fp[up], fp[idx], fp[dn]);
     OUT(TEMD_OUT_EPDIV)[idx] = epdiv;
-    OUT(TEMD_OUT_UTENDEPFD)[idx] = epdiv * iacos;
+    OUT(TEMD_OUT_UTENDEPFD)[idx] = epdiv * iacos;                                     // :753
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +217,6 @@ struct TrDev {
     double p0, a, H;
 };
 #define TOUT(q) (e.out + (size_t)(q) * e.plane)
-enum { TS_MPHICOS = TEMD_NTROUT, TS_MP = TEMD_NTROUT + 1 };
 
 __device__ __forceinline__ bool tr_index(const TrDev& e, int& t, int& k, int& m, size_t& idx) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,44 +228,55 @@ __device__ __forceinline__ bool tr_index(const TrDev& e, int& t, int& k, int& m,
     return true;
 }
 
-__global__ void k_tr_a(const TrDev e) {
+// d qb / dp (:604) and d (qb cos) / dlat (:608) at an arbitrary point
+__device__ __forceinline__ double tr_dqb_dp(const TrDev& e, size_t idx, int k) {
+    const double* qb = e.zmq;
+    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
+    return grad3(e.ap, k, qb[up], qb[idx], qb[dn]);
+}
+__device__ __forceinline__ double tr_dqbc_dlat(const TrDev& e, size_t idx, int m) {
+    const double* qb = e.zmq;
+    const double qbc = qb[idx] * e.coslat[m];
+    const double qbc_m = (m > 0) ? qb[idx - 1] * e.coslat[m - 1] : qbc;
+    const double qbc_p = (m < e.nlat - 1) ? qb[idx + 1] * e.coslat[m + 1] : qbc;
+    return grad3(e.al, m, qbc_m, qbc, qbc_p);
+}
+__device__ __forceinline__ double tr_etfy(const TrDev& e, size_t idx, int k, int m) {
+    return ((tr_dqb_dp(e, idx, k) * e.psi[idx] - e.zmq[e.plane + idx]) * (e.a * e.coslat[m])) * (e.p[k] / e.p0);   // :825-826
+}
+__device__ __forceinline__ double tr_etfz(const TrDev& e, size_t idx, int m) {
+    const double acos = e.a * e.coslat[m];
+    const double xq = -(tr_dqbc_dlat(e, idx, m) * (1.0 / acos));                      // :859
+    return -e.H / e.p0 * ((xq * e.psi[idx] - e.zmq[2 * e.plane + idx]) * acos);      // :860
+}
+
+// ONE launch per tracer: the flux-divergence neighbours (M_phi cos(phi) at lat +-1, M_p at lev +-1, :893-899) are
+// re-evaluated from qb / psi instead of being staged through scratch planes.
+__global__ void k_tr(const TrDev e) {
     int t, k, m; size_t idx;
     if (!tr_index(e, t, k, m, idx)) return;
     const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
-    const double* qb = e.zmq;
-    const double* qpvpb = e.zmq + e.plane;
-    const double* qpwappb = e.zmq + 2 * e.plane;
+    const size_t lm = (m > 0) ? idx - 1 : idx, lp = (m < e.nlat - 1) ? idx + 1 : idx;
+    const int mm = (m > 0) ? m - 1 : m, mp = (m < e.nlat - 1) ? m + 1 : m;
+    const int km = (k > 0) ? k - 1 : k, kp = (k < e.nlev - 1) ? k + 1 : k;
     const double c0 = e.coslat[m], pk = e.p[k];
-    const double acos = e.a * c0, iacos = 1.0 / (e.a * c0);
-    const double dqb_dp = grad3(e.ap, k, qb[up], qb[idx], qb[dn]);                      // :604
-    const double qbc = qb[idx] * c0;                                                  // :606
-    const double qbc_m = (m > 0) ? qb[idx - 1] * e.coslat[m - 1] : qbc;
-    const double qbc_p = (m < e.nlat - 1) ? qb[idx + 1] * e.coslat[m + 1] : qbc;
-    const double dqbc_dlat = grad3(e.al, m, qbc_m, qbc, qbc_p);                       // :608
-    const double psi = e.psi[idx];
-    const double etfy = ((dqb_dp * psi - qpvpb[idx]) * acos) * (pk / e.p0);           // :825-826
-    const double xq = -(dqbc_dlat * iacos);                                           // :859
-    const double etfz = -e.H / e.p0 * ((xq * psi - qpwappb[idx]) * acos);             // :860
+    const double iacos = 1.0 / (e.a * c0);
+    const double dqb_dp = tr_dqb_dp(e, idx, k);
+    const double dqbc_dlat = tr_dqbc_dlat(e, idx, m);
+    const double etfy = tr_etfy(e, idx, k, m);
+    const double etfz = tr_etfz(e, idx, m);
+    auto mphicos = [&](size_t i, int mi) { return (tr_etfy(e, i, k, mi) * (e.p0 / pk)) * e.coslat[mi]; };   // :893, :896
+    auto mpp = [&](size_t i) { return tr_etfz(e, i, m) * -e.p0 / e.H; };                                      // :894
+    (void)km; (void)kp;
+    const double etdiv = grad3(e.al, m, mphicos(lm, mm), (etfy * (e.p0 / pk)) * c0, mphicos(lp, mp)) * iacos
+                       + grad3(e.ap, k, mpp(up), etfz * -e.p0 / e.H, mpp(dn));                               // :897-899
     TOUT(TEMD_TROUT_DQB_DP)[idx] = dqb_dp;
-    TOUT(TEMD_TROUT_QBCOSLAT)[idx] = qbc;
+    TOUT(TEMD_TROUT_QBCOSLAT)[idx] = e.zmq[idx] * c0;                                 // :606
     TOUT(TEMD_TROUT_DQBCOSLAT_DLAT)[idx] = dqbc_dlat;
     TOUT(TEMD_TROUT_ETFY)[idx] = etfy;
     TOUT(TEMD_TROUT_ETFZ)[idx] = etfz;
     TOUT(TEMD_TROUT_QTENDVTEM)[idx] = -e.vtem[idx] * (dqbc_dlat * iacos);             // :958-959
     TOUT(TEMD_TROUT_QTENDWTEM)[idx] = -e.omegatem[idx] * dqb_dp;                      // :986-987
-    TOUT(TS_MPHICOS)[idx] = (etfy * (e.p0 / pk)) * c0;                                // :893, :896
-    TOUT(TS_MP)[idx] = etfz * -e.p0 / e.H;                                            // :894
-}
-
-__global__ void k_tr_b(const TrDev e) {
-    int t, k, m; size_t idx;
-    if (!tr_index(e, t, k, m, idx)) return;
-    const size_t up = (k > 0) ? idx - e.ld : idx, dn = (k < e.nlev - 1) ? idx + e.ld : idx;
-    const size_t lm = (m > 0) ? idx - 1 : idx, lp = (m < e.nlat - 1) ? idx + 1 : idx;
-    const double* mc = TOUT(TS_MPHICOS);
-    const double* mp = TOUT(TS_MP);
-    const double iacos = 1.0 / (e.a * e.coslat[m]);
-    const double etdiv = grad3(e.al, m, mc[lm], mc[idx], mc[lp]) * iacos + grad3(e.ap, k, mp[up], mp[idx], mp[dn]);   // :897-899
     TOUT(TEMD_TROUT_ETDIV)[idx] = etdiv;
     TOUT(TEMD_TROUT_QTENDETFD)[idx] = etdiv * iacos;                                  // :928
 }
@@ -265,8 +291,7 @@ int launch_tracer_epilogue(const temd_tracer_args& a, cudaStream_t stream) {
     e.p0 = a.p0; e.a = a.a; e.H = a.H;
     const size_t total = (size_t)a.nt * a.nlev * a.nlat;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    k_tr_a<<<blocks, 256, 0, stream>>>(e);
-    k_tr_b<<<blocks, 256, 0, stream>>>(e);
+    k_tr<<<blocks, 256, 0, stream>>>(e);
     return (int)cudaGetLastError();
 }
 
@@ -283,16 +308,14 @@ int launch_tem_epilogue(const EpilogueArgs& wrap, cudaStream_t stream) {
     e.p0 = a.p0; e.a = a.a; e.H = a.H; e.g0 = a.g0; e.pi = a.pi;
     const size_t total = (size_t)a.nt * a.nlev * a.nlat;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    k_epi_a<<<blocks, 256, 0, stream>>>(e);
     {
         const int smem = 2 * SCAN_MAXLEV * SCAN_LATS * (int)sizeof(double);
-        const cudaError_t ea = cudaFuncSetAttribute(k_epi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device
+        const cudaError_t ea = cudaFuncSetAttribute(k_epi_1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device
         if (ea != cudaSuccess) return (int)ea;
         const unsigned grid = (unsigned)(((a.nlat + SCAN_LATS - 1) / SCAN_LATS) * (size_t)a.nt);
-        k_epi_scan<<<grid, 256, smem, stream>>>(e);
+        k_epi_1<<<grid, 256, smem, stream>>>(e);
     }
-    k_epi_b<<<blocks, 256, 0, stream>>>(e);
-    k_epi_c<<<blocks, 256, 0, stream>>>(e);
+    k_epi_2<<<blocks, 256, 0, stream>>>(e);
     return (int)cudaGetLastError();
 }
 

@@ -209,6 +209,45 @@ class Engine:
         _lib.check(rc, 'temd_eddy_flux_project')
         return out
 
+    # ---- _decompose_zm_eddy + _compute_fluxes (tem_diagnostics.py:510-558) as coefficient blocks ----
+    def tem_coefficients(self, xs, lev_scale, nlev):
+        """xs = (u, v, T, omega) as [rows][N] device tensors -> ([4][rows][lpad] coefficients of ub, vb, thetab, wapb,
+        [3][rows][lpad] coefficients of upvpb, upwappb, vptpb)."""
+        c4 = self.project(list(xs[:4]), lev_scale=lev_scale, scale_field=2, nlev=nlev)
+        if self.lpad <= 408:
+            return c4, self.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, nlev)
+        # L + 1 > 408: the coefficient tile of the fused kernel no longer fits in shared memory.  Staged GPU path:
+        # native means -> eddies -> products -> projections (eddies ARE materialised, a slab at a time).
+        eu = self.eddy_native(xs[0], c4[0])
+        ev = self.eddy_native(xs[1], c4[1])
+        ew = self.eddy_native(xs[3], c4[3])
+        prods = [self.multiply(eu, ev), self.multiply(eu, ew)]
+        et = self.eddy_native(xs[2], c4[2], lev_scale, nlev)
+        prods.append(self.multiply(ev, et))
+        del et, eu, ev, ew
+        return c4, self.project(prods)
+
+    def tracer_coefficients(self, qs, xs, c4, lev_scale, nlev):
+        """Tracer TEM inputs (tem_diagnostics.py:532-538,560-570).  qs: list of [rows][N] tracers; xs, c4 as in
+        tem_coefficients.  Returns [3 * len(qs)][rows][lpad]: per tracer the coefficients of qb, qpvpb, qpwappb.
+        All tracers are projected in one launch; the fused kernel then runs per tracer on (q, v, theta, omega), whose
+        first two product slots are q'v' and q'omega'."""
+        rows = xs[0].shape[0]
+        out = torch.empty((3 * len(qs), rows, self.lpad), dtype=torch.float64, device=self.device)
+        cq_all = torch.cat([self.project(list(qs[i:i + 8])) for i in range(0, len(qs), 8)], 0)
+        ev = ew = None
+        for i, q in enumerate(qs):
+            out[3 * i] = cq_all[i]
+            if self.lpad <= 408:
+                c4q = torch.cat([cq_all[i:i + 1], c4[1:]], 0)
+                out[3 * i + 1:3 * i + 3] = self.eddy_flux_project(q, xs[1], xs[2], xs[3], c4q, lev_scale, nlev)[:2]
+            else:
+                if ev is None:
+                    ev, ew = self.eddy_native(xs[1], c4[1]), self.eddy_native(xs[3], c4[3])
+                eq = self.eddy_native(q, cq_all[i])
+                out[3 * i + 1:3 * i + 3] = self.project([self.multiply(eq, ev), self.multiply(eq, ew)])
+        return out
+
     def tem_epilogue(self, zm, p_pa, f, coslat, p0=P0):
         """zm: [7][nt][nlev][Mld-strided M] device tensor (as returned by synth_out on a [7][nt*nlev][lpad]
         coefficient block).  Returns dict name -> [nt][nlev][M] device tensors."""
@@ -275,3 +314,172 @@ class Engine:
                                             _ptr(lat_rad_dev), _ptr(lon_rad_dev), _ptr(plev_dev), self.stream)
         _lib.check(rc, 'temd_synth_fields')
         return out[:, :self.N]
+
+
+class DedupEngine(Engine):
+    """Structure-exploiting variant (opt-in `dedup=True`): the plan lives on the U unique values of
+    x = sin(lat); fields are reduced to per-group sums in ONE pass (csrc/temd_dedup.cu) and every tensor-core kernel
+    runs on U columns instead of N.  Same method surface and the same coefficients (to rounding) as `Engine`."""
+
+    def __init__(self, lat, lat_out, L, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('pytemdiags_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lat = np.ascontiguousarray(np.asarray(lat, dtype=np.float64))
+        self.lat_out = np.ascontiguousarray(np.asarray(lat_out, dtype=np.float64))
+        self.N, self.M, self.L = int(self.lat.shape[0]), int(self.lat_out.shape[0]), int(L)
+        self.Mld = self.M + (self.M & 1)
+        # group the columns by the exact value of the basis argument (computed like the reference: sph_zonal_mean.py:358)
+        x = np.cos(np.deg2rad(90 - self.lat))
+        xu, inv, cnt = np.unique(x, return_inverse=True, return_counts=True)
+        self.NU = int(xu.shape[0])
+        self.Uld = self.NU + (self.NU & 1)
+        self.multiplicity = self.N / self.NU
+        contiguous = bool(np.all(np.diff(inv) >= 0))
+        perm = None if contiguous else np.argsort(inv, kind='stable')
+        goff = np.concatenate([[0], np.cumsum(cnt)])
+        self._xu = xu
+        self._cnt_minmax = (int(cnt.min()), int(cnt.max()))
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+        self._perm = None if perm is None else i32(perm)
+        self._goff, self._gid = i32(goff), i32(inv)
+        self._mult = self._dev(cnt.astype(np.float64))
+        self._rsq = self._dev(1.0 / np.sqrt(cnt.astype(np.float64)))
+        self._plan = C.c_void_p(0)
+        _lib.check(self.lib.temd_plan_create(self.device.index or 0, self.NU, self.L, self.M, C.byref(self._plan)),
+                   'temd_plan_create')
+        self.lpad = self.lib.temd_plan_lpad(self._plan)
+        self.built = False
+        self.sanity = None
+        self.lock = threading.RLock()
+
+    def build_basis(self, sanity=False, weights=None):
+        if weights is not None:
+            raise RuntimeError('dedup=True is not available with the deprecated quadrature-weights inverse')
+        xu = self._dev(self._xu)
+        x_out = self._dev(np.cos(np.deg2rad(90 - self.lat_out)))
+        san = (C.c_double * 2)()
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_basis_build_dedup(self._plan, _ptr(xu), _ptr(x_out), _ptr(self._mult),
+                                                 san if sanity else None, self.stream)
+        _lib.check(rc, 'temd_basis_build_dedup')
+        self.built = True
+        if sanity:
+            self.sanity = (san[0], san[1])
+        return self
+
+    # ---- pieces on the unique grid ----
+    def group_sums(self, fields, lev_scale=None, scale_field=-1, nlev=1, with_products=False):
+        rows, ld = fields[0].shape[0], fields[0].stride(0)
+        for x in fields:
+            self._check_field(x)
+            if x.shape[0] != rows or x.stride(0) != ld:
+                raise RuntimeError('all fields must share shape and stride')
+        nplanes = _lib.GS_NPLANES if with_products else len(fields)
+        out = torch.empty((nplanes, rows, self.Uld), dtype=torch.float64, device=self.device)
+        if self.Uld != self.NU:
+            out[:, :, self.NU:].zero_()
+        ptrs = (C.c_void_p * len(fields))(*[x.data_ptr() for x in fields])
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_group_sums(ptrs, len(fields), rows, ld, _ptr(self._perm), _ptr(self._goff), self.NU,
+                                          self._cnt_minmax[1], self._cnt_minmax[0], _ptr(self._rsq), _ptr(lev_scale),
+                                          scale_field, nlev, int(with_products), _ptr(out), self.Uld, self.stream)
+        _lib.check(rc, 'temd_group_sums')
+        return out
+
+    def _project_u(self, planes):
+        """planes: [nf][rows][Uld] weighted group sums -> [nf][rows][lpad]."""
+        nf, rows = planes.shape[0], planes.shape[1]
+        coef = torch.empty((nf, rows, self.lpad), dtype=torch.float64, device=self.device)
+        ptrs = (C.c_void_p * nf)(*[planes[f].data_ptr() for f in range(nf)])
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_project(self._plan, ptrs, nf, rows, self.Uld, None, -1, 1, _ptr(coef), self.stream)
+        _lib.check(rc, 'temd_project')
+        return coef
+
+    def _synth_u(self, coef):
+        """[.., rows, lpad] -> Qw c on the unique grid, [.., rows, Uld] (= sqrt(multiplicity) * native zonal mean)."""
+        c2 = coef.reshape(-1, self.lpad)
+        out = torch.empty((c2.shape[0], self.Uld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_synth_native(self._plan, _ptr(c2), c2.shape[0], _ptr(out), self.Uld, self.stream)
+        _lib.check(rc, 'temd_synth_native')
+        return out.reshape(tuple(coef.shape[:-1]) + (self.Uld,))
+
+    def _expand(self, mw, x=None, lev_scale=None, nlev=1, alpha=0.0, beta=1.0, rsq=True):
+        rows = mw.shape[0]
+        ld = self.N + (self.N & 1)
+        out = torch.empty((rows, ld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_dedup_expand(_ptr(x), x.stride(0) if x is not None else 0, _ptr(lev_scale), nlev, _ptr(mw),
+                                            mw.stride(0), _ptr(self._gid), _ptr(self._rsq) if rsq else None, alpha, beta,
+                                            _ptr(out), ld, rows, self.N, self.stream)
+        _lib.check(rc, 'temd_dedup_expand')
+        return out[:, :self.N]
+
+    # ---- Engine surface ----
+    def project(self, fields, lev_scale=None, scale_field=-1, nlev=1):
+        out = []
+        for i in range(0, len(fields), 4):
+            gs = self.group_sums(fields[i:i + 4], lev_scale, scale_field - i if i <= scale_field < i + 4 else -1, nlev)
+            out.append(self._project_u(gs))
+        return out[0] if len(out) == 1 else torch.cat(out, 0)
+
+    def synth_native(self, coef, out=None):
+        res = self._expand(self._synth_u(coef.reshape(-1, self.lpad)))
+        if out is not None:
+            out[:, :self.N] = res
+            return out[:, :self.N]
+        return res
+
+    def eddy_native(self, x, coef, lev_scale=None, nlev=1):
+        self._check_field(x)
+        return self._expand(self._synth_u(coef), x, lev_scale, nlev, alpha=1.0, beta=-1.0)
+
+    def _flux(self, gs, c4):
+        rows = gs.shape[1]
+        mw = self._synth_u(c4)                                   # [4][rows][Uld]
+        fl = torch.empty((3, rows, self.Uld), dtype=torch.float64, device=self.device)
+        if self.Uld != self.NU:
+            fl[:, :, self.NU:].zero_()
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_dedup_flux(_ptr(gs), self.Uld, _ptr(mw), self.Uld, _ptr(self._goff), _ptr(self._rsq), rows,
+                                          self.NU, _ptr(fl), self.Uld, self.stream)
+        _lib.check(rc, 'temd_dedup_flux')
+        return self._project_u(fl)
+
+    def tem_coefficients(self, xs, lev_scale, nlev):
+        gs = self.group_sums(list(xs[:4]), lev_scale, 2, nlev, with_products=True)      # the ONE pass over the fields
+        c4 = self._project_u(gs[_lib.GS_SW:_lib.GS_SW + 4])
+        return c4, self._flux(gs, c4)
+
+    def eddy_flux_project(self, u, v, t, w, coef4, lev_scale, nlev):
+        gs = self.group_sums([u, v, t, w], lev_scale, 2, nlev, with_products=True)
+        return self._flux(gs, coef4)
+
+    def tracer_coefficients(self, qs, xs, c4, lev_scale, nlev):
+        rows = xs[0].shape[0]
+        out = torch.empty((3 * len(qs), rows, self.lpad), dtype=torch.float64, device=self.device)
+        for i, q in enumerate(qs):
+            gs = self.group_sums([q, xs[1], xs[2], xs[3]], lev_scale, 2, nlev, with_products=True)
+            cq = self._project_u(gs[_lib.GS_SW:_lib.GS_SW + 1])
+            out[3 * i] = cq[0]
+            out[3 * i + 1:3 * i + 3] = self._flux(gs, torch.cat([cq, c4[1:]], 0))[:2]
+        return out
+
+    def export_matrices(self, Y0=True, Y0inv=True, Y0p=True):
+        """Dense Y0 (N,L+1), Y0inv (L+1,N), Y0p (M,L+1) of the FULL grid, expanded from the unique grid:
+        Y0[i] = Y0_u[u(i)];  pinv(Y0)[:, i] = pinv(Yw)[:, u(i)] / sqrt(n_u)  (Yw = sqrt(n) Y0_u has the same Gram matrix)."""
+        Lp = self.L + 1
+        o0 = torch.empty((self.NU, Lp), dtype=torch.float64, device=self.device) if Y0 else None
+        oi = torch.empty((Lp, self.NU), dtype=torch.float64, device=self.device) if Y0inv else None
+        op = torch.empty((self.M, Lp), dtype=torch.float64, device=self.device) if Y0p else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_basis_export(self._plan, _ptr(o0), _ptr(oi), _ptr(op), self.stream)
+        _lib.check(rc, 'temd_basis_export')
+        if o0 is not None:
+            o0 = self._expand(o0.t().contiguous(), rsq=False).t().contiguous()
+        if oi is not None:
+            oi = self._expand(oi).contiguous()
+        return o0, oi, op

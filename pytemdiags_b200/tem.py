@@ -64,10 +64,11 @@ class TEMDiagnostics:
             order ('ncol', 'plev', 'time')) and `p=`.
         p : 1-D pressure levels (hPa unless p_units='Pa') or a gridpoint pressure field in Pa that is
             constant on each level (pressure-level data).  Mandatory for raw arrays.
-        Extra keywords of this build: dims, p, p_units, time, device, slab_bytes.
+        Extra keywords of this build: dims, p, p_units, time, device, slab_bytes, dedup (structure-exploiting fast
+        path for grids with repeated latitudes, see sph_zonal_averager; default False).
         '''
         opts = dict(_DEFAULTS)
-        extra = {k: kwargs.pop(k) for k in ('dims', 'p', 'p_units', 'time', 'device', 'slab_bytes', 'lat')
+        extra = {k: kwargs.pop(k) for k in ('dims', 'p', 'p_units', 'time', 'device', 'slab_bytes', 'lat', 'dedup')
                  if k in kwargs}
         pos = list(args)
         ncol_guess = None
@@ -115,6 +116,7 @@ class TEMDiagnostics:
         self._time_in = extra.get('time')
         self._device = extra.get('device')
         self._slab_bytes = extra.get('slab_bytes')
+        self._dedup = bool(extra.get('dedup', False))
 
         self._config_dims()
 
@@ -122,7 +124,7 @@ class TEMDiagnostics:
         self.ZM = sph_zonal_averager(self._lat_native_np, self._lat_zm, self.L, grid_name=self.grid_name,
                                      grid_out_name=self.zm_grid_name, save_dest=self.map_save_dest,
                                      debug=self.debug_level > 1, overwrite=self.overwrite_map,
-                                     ncoldim=self.ncolname, device=self._device)
+                                     ncoldim=self.ncolname, device=self._device, dedup=self._dedup)
         self.ZM.sph_compute_matrices(overwrite=self.overwrite_map)
         self._zonal_mean = self.ZM.sph_zonal_mean
 
@@ -431,7 +433,7 @@ class TEMDiagnostics:
         nf = len(names)
         ld = N + (N & 1)
         zero_copy = all(self._is_native_device_layout(v, dev) for v in names)
-        fused = eng.lpad <= 408
+        fused = eng.lpad <= 408 or self._dedup
         # slab size: in-place device inputs need no staging, so the whole record goes in one launch (best wave
         # quantisation); host inputs stream through two ~2 GB staging sets
         budget = self._slab_bytes if self._slab_bytes is not None else (
@@ -443,37 +445,12 @@ class TEMDiagnostics:
         coefq = torch.empty((3 * ntr, T * K, eng.lpad), dtype=torch.float64, device=dev) if ntr else None
 
         def compute(xs, t0, t1):
-            c4 = eng.project(xs[:4], lev_scale=lev_scale, scale_field=2, nlev=K)
+            c4, cf = eng.tem_coefficients(xs[:4], lev_scale, K)
             coef[:4, t0 * K:t1 * K] = c4
-            if fused:
-                cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
-                coef[4:, t0 * K:t1 * K] = cf
-                for i in range(ntr):
-                    # tracer i (tem_diagnostics.py:532-538, 560-570): the fused kernel on (q, v, theta, omega)
-                    # returns q'v' and q'omega' in its first two product slots
-                    cq = eng.project([xs[4 + i]])
-                    c4q = torch.cat([cq, c4[1:]], 0)
-                    cfq = eng.eddy_flux_project(xs[4 + i], xs[1], xs[2], xs[3], c4q, lev_scale, K)
-                    coefq[3 * i, t0 * K:t1 * K] = cq[0]
-                    coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = cfq[:2]
-            else:
-                # L + 1 > 408: the coefficient tile of the fused kernel no longer fits in shared memory.
-                # Staged GPU path: native means -> eddies -> products -> projections (eddies ARE materialised).
-                eu = eng.eddy_native(xs[0], c4[0])
-                ev = eng.eddy_native(xs[1], c4[1])
-                ew = eng.eddy_native(xs[3], c4[3])
-                prods = [eng.multiply(eu, ev), eng.multiply(eu, ew)]
-                et = eng.eddy_native(xs[2], c4[2], lev_scale, K)
-                prods.append(eng.multiply(ev, et))
-                del et, eu
-                coef[4:, t0 * K:t1 * K] = eng.project(prods)
-                del prods
-                for i in range(ntr):
-                    cq = eng.project([xs[4 + i]])
-                    eq = eng.eddy_native(xs[4 + i], cq[0])
-                    coefq[3 * i, t0 * K:t1 * K] = cq[0]
-                    coefq[3 * i + 1:3 * i + 3, t0 * K:t1 * K] = eng.project([eng.multiply(eq, ev), eng.multiply(eq, ew)])
-                    del eq
+            coef[4:, t0 * K:t1 * K] = cf
+            if ntr:
+                # tracers (tem_diagnostics.py:532-538, 560-570): qb, q'v', q'omega' per tracer
+                coefq[:, t0 * K:t1 * K] = eng.tracer_coefficients(xs[4:], xs[:4], c4, lev_scale, K)
 
         with torch.cuda.device(dev):
             if zero_copy:

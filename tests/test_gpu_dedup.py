@@ -1,0 +1,197 @@
+"""GPU: the structure-exploiting fast path (`dedup=True`) against the dense CUDA path, the oracle
+and the outputs of the unmodified reference.  Tolerance: max|d| / max|ref| <= 1e-10 per field;
+measured differences dense vs dedup are ~1e-13."""
+import ctypes as C
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from pytemdiags_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+TOL = 1e-10
+METHODS = ('vtem', 'omegatem', 'wtem', 'psitem', 'epfy', 'epfz', 'epdiv', 'utendepfd', 'utendvtem', 'utendwtem')
+PROPS = ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb', 'dub_dp', 'dthetab_dp', 'ubcoslat',
+         'dubcoslat_dlat', 'psi', 'psicoslat', 'dpsicoslat_dlat', 'dpsi_dp', 'int_vbdp')
+TRACER = ('etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem')
+
+
+def nerr(x, ref):
+    return float(np.abs(np.asarray(x) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def _grids():
+    lat_ll, lon_ll = syn.latlon_grid(24, 48)                    # 24 groups of 48 contiguous columns (warp kernel)
+    lat_pg, lon_pg = syn.pg2_grid(6)                            # ~N/7 groups of 1..8 scattered columns (thread kernel)
+    rng = np.random.default_rng(5)
+    lat_mix = np.concatenate([np.repeat(rng.uniform(-80, 80, 9), 40), rng.uniform(-89, 89, 300),
+                              np.repeat(rng.uniform(-60, 60, 20), 3)])          # both kernels in one grid, shuffled
+    order = rng.permutation(lat_mix.shape[0])
+    lat_mix = lat_mix[order]
+    lon_mix = rng.uniform(0, 360, lat_mix.shape[0])
+    return {'latlon': (lat_ll, lon_ll, 14), 'pg2': (lat_pg, lon_pg, 20), 'mixed': (lat_mix, lon_mix, 16)}
+
+
+@pytest.mark.parametrize('grid', ['latlon', 'pg2', 'mixed'])
+def test_dedup_matches_dense_and_oracle(grid):
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon, L = _grids()[grid]
+    K, T = 7, 3
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=12, fields=('ua', 'va', 'ta', 'wap', 'q'))
+    kw = dict(L=L, dims=('time', 'lev', 'ncol'), debug_level=0, q=f['q'])
+    dense = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, **kw)
+    dd = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, dedup=True, **kw)
+    eng = dd.ZM._engine
+    assert eng.NU < eng.N and type(eng).__name__ == 'DedupEngine'
+    tr = lambda x: np.ascontiguousarray(x.transpose(2, 1, 0))
+    ref = oracle.tem_suite(tr(f['ua']), tr(f['va']), tr(f['ta']), tr(f['wap']), plev, lat, L=L)
+    worst = 0.0
+    for m in METHODS:
+        e = nerr(getattr(dd, m)(), getattr(dense, m)())
+        worst = max(worst, e)
+        assert e < TOL, (m, e)
+        assert nerr(getattr(dd, m)(), ref[m]) < TOL, m
+    for p_ in PROPS:
+        assert nerr(getattr(dd, p_), getattr(dense, p_)) < TOL, p_
+    for m in TRACER:
+        assert nerr(getattr(dd, m)(0), getattr(dense, m)(0)) < TOL, m
+    # native-grid properties rebuilt on demand go through the expand kernel
+    for p_ in ('up', 'thetap', 'vptp'):
+        assert nerr(getattr(dd, p_), getattr(dense, p_)) < TOL, p_
+    assert worst < 1e-11, worst        # in practice the two paths agree far better than the bar
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(HERE, 'golden', 'tem_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_dedup_against_reference_outputs(path):
+    """The fixtures computed by the unmodified reference (pg2 grids and the raveled lat-lon grid of tem_util.py:331)."""
+    from _xarray_shim import DataArray
+    from pytemdiags_b200 import TEMDiagnostics
+    g = np.load(path)
+    dims = tuple(str(d) for d in g['dims'])
+    coords = {'plev': g['plev_in'], 'time': g['time']}
+    da = {n: DataArray(g['in_' + n], dims=dims, coords=coords, name=n) for n in ('ua', 'va', 'ta', 'wap')}
+    lat = DataArray(g['lat'], dims=('ncol',), name='lat')
+    kw = {} if float(g['zm_dlat']) == 1 else {'zm_dlat': int(g['zm_dlat'])}
+    if 'in_q' in g:
+        kw['q'] = DataArray(g['in_q'], dims=dims, coords=coords, name='q')
+    tem = TEMDiagnostics(da['ua'], da['va'], da['ta'], da['wap'], lat, L=int(g['L']), debug_level=0, dedup=True, **kw)
+    assert tem.ZM._engine.NU < tem.ZM._engine.N
+    for m in METHODS:
+        assert nerr(getattr(tem, m)().values, g['ref_' + m]) < TOL, (m, nerr(getattr(tem, m)().values, g['ref_' + m]))
+    for p_ in PROPS:
+        assert nerr(getattr(tem, p_).values, g['ref_' + p_]) < TOL, p_
+    if 'in_q' in g:
+        for m in TRACER:
+            assert nerr(getattr(tem, m)().values, g['ref_' + m + '0']) < TOL, m
+    A = da['ua'].transpose('ncol', 'plev', 'time')
+    assert nerr(tem.ZM.sph_zonal_mean(A).values, g['ref_zm_ua']) < TOL
+    assert nerr(tem.ZM.sph_zonal_mean_native(A).values, g['ref_zmnative_ua']) < TOL
+    assert nerr(tem.ZM.Y0inv, g['ref_Y0inv']) < TOL
+
+
+def test_dedup_averager_matrices_and_means():
+    from pytemdiags_b200 import sph_zonal_averager
+    lat, lon = syn.latlon_grid(30, 64, poles=False)
+    lat_out = np.arange(-87.0, 88.0, 3.0)
+    L = 12
+    ZM = sph_zonal_averager(lat, lat_out, L, dedup=True)
+    ZM.sph_compute_matrices()
+    Y0, Y0inv, Y0p = oracle.sph_matrices(lat, lat_out, L)
+    assert nerr(ZM.Y0, Y0) < 1e-12 and nerr(ZM.Y0p, Y0p) < 1e-12 and nerr(ZM.Y0inv, Y0inv) < TOL
+    A = np.random.default_rng(1).standard_normal((lat.shape[0], 4, 3))
+    assert nerr(ZM.sph_zonal_mean(A), oracle.zonal_mean(A, Y0p, Y0inv)) < TOL
+    assert nerr(ZM.sph_zonal_mean_native(A), oracle.zonal_mean(A, Y0, Y0inv)) < TOL
+    # 5 fields at once exercise the 4-field chunking of the group-sum kernel
+    eng = ZM._engine
+    import torch
+    xs = [torch.as_tensor(np.ascontiguousarray(A[:, :, 0].T) * (i + 1)).cuda() for i in range(5)]
+    c = eng.project(xs)
+    assert tuple(c.shape) == (5, 4, eng.lpad)
+    assert nerr(c[4].cpu().numpy(), 5 * c[0].cpu().numpy()) < 1e-13
+    with pytest.raises(RuntimeError, match='weights'):
+        sph_zonal_averager(lat, lat_out, L, dedup=True, weights=np.full(lat.shape[0], 1.0 / lat.shape[0]))
+
+
+def test_group_sums_c_abi_against_numpy(temd_lib):
+    """temd_group_sums through the C ABI on a grid with group sizes 1 .. 70 (both kernels), with and without products."""
+    import torch
+    rng = np.random.default_rng(7)
+    cnt = np.concatenate([rng.integers(1, 32, 40), rng.integers(32, 71, 6)])
+    gid = rng.permutation(np.repeat(np.arange(cnt.shape[0]), cnt))
+    N, U = gid.shape[0] + (gid.shape[0] & 1), cnt.shape[0]
+    n = gid.shape[0]
+    rows, nlev = 10, 5
+    perm = np.argsort(gid, kind='stable')
+    goff = np.concatenate([[0], np.cumsum(cnt)])
+    X = rng.standard_normal((4, rows, N)) + np.array([30.0, 1.0, 250.0, 0.01])[:, None, None]
+    sc = rng.uniform(1.0, 7.0, nlev)
+    d = lambda a, dt=None: torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).cuda()
+    xs = [d(X[f]) for f in range(4)]
+    Uld = U + (U & 1)
+    out = torch.zeros((15, rows, Uld), dtype=torch.float64, device='cuda')
+    ptrs = (C.c_void_p * 4)(*[x.data_ptr() for x in xs])
+    dperm, dgoff, drsq, dsc = d(perm, np.int32), d(goff, np.int32), d(1 / np.sqrt(cnt)), d(sc)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = temd_lib.temd_group_sums(ptrs, 4, rows, N, C.c_void_p(dperm.data_ptr()), C.c_void_p(dgoff.data_ptr()), U,
+                                  int(cnt.max()), int(cnt.min()), C.c_void_p(drsq.data_ptr()), C.c_void_p(dsc.data_ptr()),
+                                  2, nlev, 1, C.c_void_p(out.data_ptr()), Uld, st)
+    assert rc == 0, temd_lib.temd_last_error()
+    got = out.cpu().numpy()[:, :, :U]
+    Xs = X[:, :, :n].copy()
+    Xs[2] *= sc[np.arange(rows) % nlev][:, None]
+    pairs = ((0, 1), (0, 3), (1, 2))
+    for u in range(U):
+        cols = perm[goff[u]:goff[u + 1]]
+        a0 = Xs[:, :, cols[0]]
+        dlt = Xs[:, :, cols] - a0[:, :, None]
+        assert np.array_equal(got[0:4, :, u], a0)
+        assert np.allclose(got[4:8, :, u], dlt.sum(-1), rtol=1e-12, atol=1e-12)
+        for q, (a, b) in enumerate(pairs):
+            assert np.allclose(got[8 + q, :, u], (dlt[a] * dlt[b]).sum(-1), rtol=1e-12, atol=1e-12)
+        assert np.allclose(got[11:15, :, u], Xs[:, :, cols].sum(-1) / np.sqrt(cnt[u]), rtol=1e-13)
+    # sums only, 2 fields, and bit-for-bit reproducibility
+    out2 = torch.zeros((2, rows, Uld), dtype=torch.float64, device='cuda')
+    out3 = torch.zeros_like(out2)
+    for o in (out2, out3):
+        rc = temd_lib.temd_group_sums(ptrs, 2, rows, N, C.c_void_p(dperm.data_ptr()), C.c_void_p(dgoff.data_ptr()), U,
+                                      int(cnt.max()), int(cnt.min()), C.c_void_p(drsq.data_ptr()), None, -1, 1, 0,
+                                      C.c_void_p(o.data_ptr()), Uld, st)
+        assert rc == 0
+    assert torch.equal(out2, out3)
+    for u in range(U):
+        cols = perm[goff[u]:goff[u + 1]]
+        assert np.allclose(out2.cpu().numpy()[:, :, u], X[:2][:, :, cols].sum(-1) / np.sqrt(cnt[u]), rtol=1e-13)
+
+
+def test_dedup_config4_one_step():
+    """config 4 (721 x 1440 lat-lon raveled lat-major, L=300) at full column count, one time step, against the
+    expectation precomputed by the CPU oracle (tests/golden/make_scale_golden.py)."""
+    from pytemdiags_b200 import TEMDiagnostics
+    path = os.path.join(HERE, 'golden', 'scale_config4_t1.npz')
+    if not os.path.exists(path):
+        pytest.skip('fixture not generated')
+    g = np.load(path)
+    grid = tuple(g['grid'].tolist())
+    grid = (grid[0],) + tuple(int(x) for x in grid[1:])
+    K, L, seed, t0 = int(g['K']), int(g['L']), int(g['seed']), int(g['t0'])
+    lat, lon = syn.make_grid(grid)
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, 1, seed=seed, t0=t0)
+    tem = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=L, dims=('time', 'lev', 'ncol'), debug_level=0,
+                         dedup=True)
+    assert tem.ZM._engine.NU == 721
+    bad = {}
+    for n in oracle.TEM_OUTPUTS + ('ub', 'vb', 'thetab', 'wapb', 'upvpb', 'upwappb', 'vptpb'):
+        got = getattr(tem, n)
+        e = nerr(got() if callable(got) else got, g[n])
+        if not e < TOL:
+            bad[n] = e
+    assert not bad, bad
