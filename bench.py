@@ -512,11 +512,19 @@ def run_record(ctx, cfgname, sub_steps, dedup=False):
         coef[:4, r0:r1] = c4
         coef[4:, r0:r1] = cf
 
+    host_ms = {}
+
     def tail():
-        eng.check_finite(coef, 'fields')
-        zm = eng.synth_out(coef).reshape(7, b - a, K, eng.M)
-        res = eng.tem_epilogue(zm, p_pa, f_zm, coslat)
-        full = gather_time_major(torch.stack([res[n] for n in PUBLIC]), T) if ctx.world > 1 else None
+        h0 = time.time()
+        timed('tail_check_finite', lambda: eng.check_finite(coef, 'fields'))
+        h1 = time.time()
+        zm = timed('tail_synth_out', lambda: eng.synth_out(coef)).reshape(7, b - a, K, eng.M)
+        h2 = time.time()
+        res = timed('tail_epilogue', lambda: eng.tem_epilogue(zm, p_pa, f_zm, coslat))
+        h3 = time.time()
+        full = timed('tail_gather', lambda: gather_time_major(torch.stack([res[n] for n in PUBLIC]), T)) if ctx.world > 1 else None
+        host_ms.update(check_finite=(h1 - h0) * 1e3, synth_out=(h2 - h1) * 1e3, epilogue=(h3 - h2) * 1e3,
+                       gather=(time.time() - h3) * 1e3)
         return res, full
 
     starts = list(range(a, b, sub_steps))
@@ -530,7 +538,7 @@ def run_record(ctx, cfgname, sub_steps, dedup=False):
     res, full = timed('tail', tail)
     ctx.barrier()
     kms = {n: float(np.sum([x.elapsed_time(y) for x, y in v])) for n, v in ev.items()}
-    local_ms = sum(kms.values())
+    local_ms = sum(v for n, v in kms.items() if not n.startswith('tail_'))
     total_ms = ctx.max(local_ms)
     kmax = {n: ctx.max(v) for n, v in sorted(kms.items())}
     check = spot_check(ctx, cfgname, res, a, b - a)
@@ -540,7 +548,7 @@ def run_record(ctx, cfgname, sub_steps, dedup=False):
                                                                          'dedup fast path' if dedup else 'dense path'),
            'scaling': 'strong', 'time_steps_per_gpu': [y - x for x, y in shard_bounds(T, ctx.world)], 'sub_slab_steps': sub_steps,
            'record_ms': total_ms, 'value': pts / (total_ms * 1e-3), 'unit': UNIT, 'kernel_ms_max_over_ranks': kmax,
-           'basis_build_s': basis_s, 'spot_check': check,
+           'basis_build_s': basis_s, 'spot_check': check, 'tail_host_ms': {k_: round(v, 3) for k_, v in host_ms.items()},
            'timing': 'CUDA events around every suite launch of every slab + the tail (synth_out, epilogue, all-gather); '
                      'on-device slab generation between slabs is not timed; max over ranks'}
     if dedup:

@@ -88,3 +88,25 @@ def test_config5_zonal_mean_sweep(L):
     assert nerr(ZM.sph_zonal_mean_native(zn, ncol_last=True), zn) < 1e-11
     h = np.roll(f, 7, axis=1) * 0.37
     assert nerr(ZM.sph_zonal_mean(f + h, ncol_last=True), zm + ZM.sph_zonal_mean(h, ncol_last=True)) < 1e-11
+
+
+def test_config4_y0inv_against_svd_pinv():
+    """config 4 (1,038,240 columns, L=300, cond(Y0) ~ 19): 64 sampled columns of the exported Y0inv against
+    numpy's SVD pseudo-inverse of the full Y0.  The one-step fixtures above were computed with the normal-equations
+    inverse, i.e. the same algebra as the GPU's whitened basis; this check decouples the expectation from it
+    (measured agreement ~1e-13, as bounded by cond(Y0)^2 eps)."""
+    from pytemdiags_b200 import sph_zonal_averager
+    lat, lon = syn.latlon_grid(721, 1440)
+    L = 300
+    lat1 = np.linspace(-90, 90, 721)
+    Y0 = np.repeat(oracle.sph_basis(lat1, L), 1440, axis=0)             # rows depend on latitude only
+    assert np.array_equal(np.repeat(lat1, 1440), lat)
+    Y0inv_ref = np.linalg.pinv(Y0)                                      # SVD (gesdd), default rcond
+    ZM = sph_zonal_averager(lat, oracle.zm_latitudes(1), L)
+    ZM.sph_compute_matrices()
+    cols = np.random.default_rng(0).choice(lat.shape[0], 64, replace=False)
+    got = ZM.Y0inv[:, cols]
+    assert nerr(got, Y0inv_ref[:, cols]) < TOL, nerr(got, Y0inv_ref[:, cols])
+    ZD = sph_zonal_averager(lat, oracle.zm_latitudes(1), L, dedup=True)
+    ZD.sph_compute_matrices()
+    assert nerr(ZD.Y0inv[:, cols], Y0inv_ref[:, cols]) < TOL
