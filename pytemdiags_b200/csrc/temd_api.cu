@@ -187,7 +187,7 @@ struct temd_plan {
     double *rec_a, *rec_b;   // recurrence coefficients [L+1]
     double *x, *x_out;       // copies of the node coordinates (for exports)
     std::mutex* work_mu;     // split-K partials: one workspace per stream, so a plan is re-entrant per (device, stream)
-    std::map<cudaStream_t, std::pair<double*, size_t>>* work;
+    std::map<std::pair<cudaStream_t, int>, std::pair<double*, size_t>>* work;   // slot 0: split-K partials, 1: eddy scratch
     int* status;
     double* sanity;
     bool built;
@@ -196,9 +196,9 @@ struct temd_plan {
 
 // Split-K workspace of `stream` (grown on demand).  Work already enqueued on that stream may still use the old
 // buffer when it grows: cudaFree synchronises the device before releasing it.
-static int ensure_work(temd_plan* p, cudaStream_t stream, size_t doubles, double** out) {
+static int ensure_work(temd_plan* p, cudaStream_t stream, size_t doubles, double** out, int slot = 0) {
     std::lock_guard<std::mutex> lock(*p->work_mu);
-    auto& w = (*p->work)[stream];
+    auto& w = (*p->work)[std::make_pair(stream, slot)];
     if (doubles > w.second) {
         if (w.first) TEMD_CUDA(cudaFree(w.first));
         w.first = nullptr;
@@ -228,7 +228,7 @@ extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_
     temd_plan* p = new temd_plan();
     memset(p, 0, sizeof(*p));
     p->work_mu = new std::mutex();
-    p->work = new std::map<cudaStream_t, std::pair<double*, size_t>>();
+    p->work = new std::map<std::pair<cudaStream_t, int>, std::pair<double*, size_t>>();
     p->dev = device; p->N = ncol; p->L = L; p->Lp = L + 1; p->M = nlat_out;
     p->lpad = (int)round_up(L + 1, 8);
     p->sms = prop.multiProcessorCount;
@@ -529,18 +529,63 @@ extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const doubl
     if (p == nullptr || !p->built) return temd_set_error(-1, "eddy_flux_project: basis not built");
     if (!u || !v || !t || !w || !coef4 || !coef_flux || rows < 1 || ld < (size_t)p->N)
         return temd_set_error(-1, "eddy_flux_project: bad arguments");
-    if (!eddy_supported(p->lpad)) return temd_set_error(-1, "eddy_flux_project: L = %d too large for the fused kernel (max 407)", p->L);
     if (p->weighted) return temd_set_error(-1, "eddy_flux_project: not available with the quadrature-weights inverse (TEMDiagnostics never uses it)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     TEMD_ON_DEVICE(p->dev);
     const int nchunks = (p->N + 15) / 16;
-    const int nsplit = eddy_pick_split(rows, p->lpad, nchunks, p->sms);
-    double* work = nullptr;
-    int rc = ensure_work(p, st, eddy_workspace_doubles(rows, p->lpad, nsplit), &work);
-    if (rc) return rc;
     const double* x4[4] = {u, v, t, w};
-    return launch_eddy_flux_project(x4, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef4, coef_flux, work, nsplit,
-                                    lev_scale, nlev, st);
+    // Two implementations of the same contraction (results agree to rounding):
+    //   fused  one kernel, eddies and products never leave the SM (k_eddy): best while the 4 x 32 x lpad coefficient
+    //          tile fits in shared memory (L + 1 <= 104), 32 B of HBM traffic per point;
+    //   split  k_synth with the eddy epilogue writes the four eddy fields of a row batch to a scratch buffer,
+    //          k_project in product mode reads them back and projects u'v', u'omega', v'theta' (96 B per point, still far
+    //          below the FP64 roofline for L >= 104): both are plain GEMM pipelines whose tile shapes do not shrink with L.
+    const int mode = [] {          // read at every call: lets one process A/B both implementations
+        const char* e = getenv("TEMD_EDDY_MODE");
+        return (e && !strcmp(e, "fused")) ? 1 : (e && !strcmp(e, "split")) ? 2 : 0;
+    }();
+    const bool can_fuse = eddy_supported(p->lpad);
+    const bool split = (mode == 2) || !can_fuse || (mode == 0 && p->lpad > 104);
+    if (!split) {
+        const int nsplit = eddy_pick_split(rows, p->lpad, nchunks, p->sms);
+        double* work = nullptr;
+        int rc = ensure_work(p, st, eddy_workspace_doubles(rows, p->lpad, nsplit), &work);
+        if (rc) return rc;
+        return launch_eddy_flux_project(x4, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef4, coef_flux, work, nsplit,
+                                        lev_scale, nlev, st);
+    }
+    // ---- split path, in row batches bounded by the scratch budget
+    const double scratch_gb = [] { const char* e = getenv("TEMD_EDDY_SCRATCH_GB"); return (e && atof(e) > 0) ? atof(e) : 16.0; }();
+    const size_t ld_e = round_up(p->N, 2);
+    size_t rb = (size_t)(scratch_gb * 1073741824.0 / (4.0 * ld_e * sizeof(double)));
+    rb = rb / 128 * 128;
+    if (rb < 128) rb = 128;
+    if (rb > (size_t)rows) rb = rows;
+    double* scratch = nullptr;
+    int rc = ensure_work(p, st, 4 * rb * ld_e, &scratch, 1);
+    if (rc) return rc;
+    double* e4[4] = {scratch, scratch + rb * ld_e, scratch + 2 * rb * ld_e, scratch + 3 * rb * ld_e};
+    int ntb, lblocks;
+    project_lblocks(p->lpad, &ntb, &lblocks);
+    for (size_t r0 = 0; r0 < (size_t)rows; r0 += rb) {
+        const int nr = (int)std::min(rb, (size_t)rows - r0);
+        const double* xb[4] = {u + r0 * ld, v + r0 * ld, t + r0 * ld, w + r0 * ld};
+        if ((rc = launch_synth_eddy4(coef4, rows, (int)r0, nr, p->lpad, p->qt, p->N, p->ld_q, xb, ld, lev_scale, nlev, e4, ld_e, st)))
+            return rc;
+        const int tiles = ((nr + 127) / 128) * 3;
+        const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 64);
+        const size_t part_d = project_workspace_doubles(3, nr, p->lpad, nsplit), tmp_d = (size_t)3 * nr * p->lpad;
+        double* work = nullptr;
+        if ((rc = ensure_work(p, st, part_d + tmp_d, &work))) return rc;
+        const double* pairs[6] = {e4[0], e4[1], e4[0], e4[3], e4[1], e4[2]};   // u'v', u'omega', v'theta'
+        double* tmp = (nr == rows) ? coef_flux : work + part_d;
+        if ((rc = launch_project_products(pairs, 3, nr, p->N, ld_e, p->qt, p->lpad, p->ld_q, tmp, work, nsplit, st))) return rc;
+        if (nr != rows)
+            TEMD_CUDA(cudaMemcpy2DAsync(coef_flux + r0 * p->lpad, (size_t)rows * p->lpad * sizeof(double), tmp,
+                                        (size_t)nr * p->lpad * sizeof(double), (size_t)nr * p->lpad * sizeof(double), 3,
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
 }
 
 extern "C" int temd_tem_epilogue(temd_plan* p, const temd_epilogue_args* args, void* stream) {

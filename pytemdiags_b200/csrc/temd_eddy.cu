@@ -7,8 +7,9 @@
 // The reference materialises 4 native means, 4 eddies and 3 products (11 N x K x T arrays); here
 // none of them reaches HBM.  Per CTA: BM (time,lev) rows, a split-K range of 16-column chunks.
 //
-//   per chunk:  GEMM1  S_f[BM x 16] = C_f[BM x lpad] * QT[lpad x 16]      f = u, v, theta, omega
-//               E_f = X_f - S_f   (theta: X = lev_scale * T), written in place over the X tile
+//   per chunk:  GEMM1  E_f[BM x 16] = X_f - C_f[BM x lpad] * QT[lpad x 16]   f = u, v, theta, omega (theta: X = lev_scale * T;
+//                      the accumulators start from the X tile and the resident coefficients are negated),
+//               E_f written in place over the X tile
 //               GEMM2  acc_g[BM x lpad] += (E_a .* E_b)[BM x 16] * QT^T[16 x lpad]   g = uv, uw, v.theta
 //
 // Both GEMMs are DMMA.8x8x4; the QT chunk tile ([lpad rows][16 cols], TMA, 128-B swizzle) is the
@@ -176,7 +177,8 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
         const int row = row0 + r;
         const double* src = p.coef4 + ((size_t)f * p.rows + row) * lpad;
         double* dst = Cs + (size_t)fr * p.ls;
-        for (int l = lane; l < lpad; l += 32) dst[l] = (row < p.rows) ? src[l] : 0.0;
+        // NEGATED: GEMM1 then accumulates x - C*QT directly on top of the X tile values (see round())
+        for (int l = lane; l < lpad; l += 32) dst[l] = (row < p.rows) ? -src[l] : 0.0;
     }
     (void)tid;
     named_bar_sync(15, WARPS * 32);
@@ -241,14 +243,23 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
             st[c] = smem_base + s * stage_bytes;
             qs[c] = st[c] + q_off;
         }
-        // ---------------- GEMM1: S = C * QT (contraction over l = QT tile rows) ----------------
+        // ---------------- GEMM1: E = X - C * QT (contraction over l = QT tile rows) ----------------
+        // The accumulators start from the X tile values (theta: lev_scale * T) and Cs holds -C, so the tensor pipe
+        // delivers the eddies themselves: no FP64 subtract per element on the pipe DMMA shares with DADD/DFMA.
         double sacc[NCH][NF1][NN1][2];
 #pragma unroll
         for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int ff = 0; ff < NF1; ff++)
+            for (int nn = 0; nn < NN1; nn++) {
+                const uint32_t off = swz_off(mi * 8 + g1, (jn1 + nn) * 8 + 2 * t);
 #pragma unroll
-                for (int nn = 0; nn < NN1; nn++) sacc[c][ff][nn][0] = sacc[c][ff][nn][1] = 0.0;
+                for (int ff = 0; ff < NF1; ff++) {
+                    double2 x = lds128(st[c] + fid[ff] * XF_BYTES + off);
+                    if (fid[ff] == 2) { x.x *= tscale; x.y *= tscale; }
+                    sacc[c][ff][nn][0] = x.x;
+                    sacc[c][ff][nn][1] = x.y;
+                }
+            }
 #pragma unroll 2
         for (int l8 = 0; l8 < p.nt; l8++) {
 #pragma unroll
@@ -284,10 +295,8 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
                 double e0[NF1], e1[NF1];
 #pragma unroll
                 for (int ff = 0; ff < NF1; ff++) {
-                    const double sc = (fid[ff] == 2) ? tscale : 1.0;
-                    const double2 x = lds128(st[c] + fid[ff] * XF_BYTES + off);
-                    e0[ff] = sc * x.x - sacc[c][ff][nn][0];
-                    e1[ff] = sc * x.y - sacc[c][ff][nn][1];
+                    e0[ff] = sacc[c][ff][nn][0];
+                    e1[ff] = sacc[c][ff][nn][1];
                 }
                 sts128(st[c] + fid[0] * XF_BYTES + off, e0[0], e1[0]);
                 if (PAIRED) sts128(st[c] + fid[NF1 - 1] * XF_BYTES + off, e0[0] * e0[NF1 - 1], e1[0] * e1[NF1 - 1]);

@@ -27,9 +27,16 @@ int launch_project(const double* const* x, int nfields, int rows, int ncol, size
                    size_t ld_q, double* out, double* part, int nsplit, const double* lev_scale, int scale_field,
                    int nlev, cudaStream_t stream);
 
+int launch_project_products(const double* const* xpairs, int npairs, int rows, int ncol, size_t ld_x, const double* qt,
+                            int lpad, size_t ld_q, double* out, double* part, int nsplit, cudaStream_t stream);
+
 // ---- generic synthesis GEMM  S[row][n] = sum_l C[row][l] * B[l][n]  (temd_synth.cu) ----
 int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b, double* out,
                  size_t ld_out, cudaStream_t stream);
+
+int launch_synth_eddy4(const double* coef4, int rows_total, int r0, int rows, int lpad, const double* b, int ncol, size_t ld_b,
+                       const double* const* x, size_t ld_x, const double* lev_scale, int nlev, double* const* out,
+                       size_t ld_out, cudaStream_t stream);
 
 int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b,
                           double* out, size_t ld_out, int sms, cudaStream_t stream);

@@ -35,21 +35,25 @@ struct ProjParams {
     double* part;        // [nsplit][nfields][rows][lpad]
 };
 
-template <int NTB>
-constexpr int proj_stage_bytes() { return (PROJ_BM + NTB * 8) * TILE_ROW_BYTES; }
+// PROD: "field" f is the element-wise product of the two arrays behind maps.x[2f] and maps.x[2f+1] (the eddy-flux
+// products u'v', u'omega', v'theta' of tem_diagnostics.py:547-555 formed on the fly from eddy fields: the product
+// arrays are never written).  A stage then holds two X tiles.
+template <int NTB, bool PROD>
+constexpr int proj_stage_bytes() { return ((PROD ? 2 : 1) * PROJ_BM + NTB * 8) * TILE_ROW_BYTES; }
 
-template <int NTB>
+template <int NTB, bool PROD>
 constexpr int proj_stages() {
-    int s = (200 * 1024) / proj_stage_bytes<NTB>();
+    int s = (200 * 1024) / proj_stage_bytes<NTB, PROD>();
     return s > 8 ? 8 : s;
 }
 
-template <int NTB, int WARPS>
+template <int NTB, int WARPS, bool PROD>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1)
 k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
     constexpr int MTW = PROJ_BM / 8 / WARPS;   // m8-tiles per consumer warp (2 with 8 warps, 1 with 16)
-    constexpr int STAGES = proj_stages<NTB>();
-    constexpr int STAGE_BYTES = proj_stage_bytes<NTB>();
+    constexpr int STAGES = proj_stages<NTB, PROD>();
+    constexpr int STAGE_BYTES = proj_stage_bytes<NTB, PROD>();
+    constexpr int XROWS = (PROD ? 2 : 1) * PROJ_BM;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-B alignment is required by the 128-B swizzle pattern
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,7 +89,7 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
     if (warp == WARPS) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            tma_prefetch_desc(&maps.x[field]);
+            tma_prefetch_desc(&maps.x[PROD ? 2 * field : field]);
             tma_prefetch_desc(&maps.q);
             for (int i = 0; i < nloc; i++) {
                 const int s = i % STAGES;
@@ -94,8 +98,13 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
                 mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
                 const uint32_t dst = smem_base + s * STAGE_BYTES;
                 const int col = (c_begin + i) * TILE_K;
-                tma_load_2d(dst, &maps.x[field], col, row0, full_bar(s));
-                tma_load_2d(dst + PROJ_BM * TILE_ROW_BYTES, &maps.q, col, l0, full_bar(s));
+                if constexpr (PROD) {
+                    tma_load_2d(dst, &maps.x[2 * field], col, row0, full_bar(s));
+                    tma_load_2d(dst + PROJ_BM * TILE_ROW_BYTES, &maps.x[2 * field + 1], col, row0, full_bar(s));
+                } else {
+                    tma_load_2d(dst, &maps.x[field], col, row0, full_bar(s));
+                }
+                tma_load_2d(dst + XROWS * TILE_ROW_BYTES, &maps.q, col, l0, full_bar(s));
             }
         }
         return;
@@ -113,7 +122,7 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) coff[kk] = kmajor_col_off(g, t, kk);
     const uint32_t a_row_off = (warp * 8 * MTW + g) * TILE_ROW_BYTES;
-    const uint32_t b_row_off = PROJ_BM * TILE_ROW_BYTES + g * TILE_ROW_BYTES;
+    const uint32_t b_row_off = XROWS * TILE_ROW_BYTES + g * TILE_ROW_BYTES;
 
     for (int i = 0; i < nloc; i++) {
         const int s = i % STAGES;
@@ -124,7 +133,10 @@ k_project(const __grid_constant__ ProjMaps maps, const ProjParams p) {
         for (int kk = 0; kk < 4; kk++) {
             double a[MTW], b[NTB];
 #pragma unroll
-            for (int i2 = 0; i2 < MTW; i2++) a[i2] = lds64(st + a_row_off + i2 * 8 * TILE_ROW_BYTES + coff[kk]);
+            for (int i2 = 0; i2 < MTW; i2++) {
+                a[i2] = lds64(st + a_row_off + i2 * 8 * TILE_ROW_BYTES + coff[kk]);
+                if constexpr (PROD) a[i2] *= lds64(st + PROJ_BM * TILE_ROW_BYTES + a_row_off + i2 * 8 * TILE_ROW_BYTES + coff[kk]);
+            }
 #pragma unroll
             for (int j = 0; j < NTB; j++) b[j] = lds64(st + b_row_off + j * 8 * TILE_ROW_BYTES + coff[kk]);
 #pragma unroll
@@ -178,20 +190,21 @@ int launch_reduce_partials(const double* part, double* out, int nsplit, int nfie
     return 0;
 }
 
-template <int NTB, int WARPS>
+template <int NTB, int WARPS, bool PROD>
 static int launch_project_w(const ProjMaps& maps, const ProjParams& p, int lblocks, cudaStream_t stream) {
-    constexpr int smem = proj_stages<NTB>() * proj_stage_bytes<NTB>() + 1024;
-    cudaError_t e = cudaFuncSetAttribute(k_project<NTB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    constexpr int smem = proj_stages<NTB, PROD>() * proj_stage_bytes<NTB, PROD>() + 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_project<NTB, WARPS, PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(p.tiles_per_field * p.nfields * p.nsplit, lblocks);
-    k_project<NTB, WARPS><<<grid, (WARPS + 1) * 32, smem, stream>>>(maps, p);
+    k_project<NTB, WARPS, PROD><<<grid, (WARPS + 1) * 32, smem, stream>>>(maps, p);
     return (int)cudaGetLastError();
 }
 
 template <int NTB>
-static int launch_project_t(const ProjMaps& maps, const ProjParams& p, int lblocks, cudaStream_t stream) {
+static int launch_project_t(const ProjMaps& maps, const ProjParams& p, int lblocks, bool prod, cudaStream_t stream) {
     static const int warps = [] { const char* e = getenv("TEMD_PROJECT_WARPS"); return (e && atoi(e) == 16) ? 16 : 8; }();   // 8 measured faster (34.3 vs 33.9 TFLOP/s)
-    return warps == 8 ? launch_project_w<NTB, 8>(maps, p, lblocks, stream) : launch_project_w<NTB, 16>(maps, p, lblocks, stream);
+    if (prod) return launch_project_w<NTB, 8, true>(maps, p, lblocks, stream);
+    return warps == 8 ? launch_project_w<NTB, 8, false>(maps, p, lblocks, stream) : launch_project_w<NTB, 16, false>(maps, p, lblocks, stream);
 }
 
 // pick the l-block size: balanced blocks of at most 13 n8-tiles
@@ -220,19 +233,20 @@ size_t project_workspace_doubles(int nfields, int rows, int lpad, int nsplit) {
 }
 
 // Host launcher.  x[f] are device pointers to [rows][ld_x] doubles (ld_x >= ncol, ld_x even);
-// qt is [lpad][ld_q].  out: [nfields][rows][lpad].
-int launch_project(const double* const* x, int nfields, int rows, int ncol, size_t ld_x, const double* qt,
-                   int lpad, size_t ld_q, double* out, double* part, int nsplit, const double* lev_scale,
-                   int scale_field, int nlev, cudaStream_t stream) {
-    if (nfields < 1 || nfields > TEMD_MAX_FIELDS) return temd_set_error(-1, "project: nfields out of range");
+// qt is [lpad][ld_q].  out: [nfields][rows][lpad].  prod: x holds 2 * nfields pointers and field f is x[2f] .* x[2f+1].
+static int launch_project_impl(const double* const* x, int nfields, bool prod, int rows, int ncol, size_t ld_x, const double* qt,
+                               int lpad, size_t ld_q, double* out, double* part, int nsplit, const double* lev_scale,
+                               int scale_field, int nlev, cudaStream_t stream) {
+    const int nmaps = prod ? 2 * nfields : nfields;
+    if (nfields < 1 || nmaps > TEMD_MAX_FIELDS) return temd_set_error(-1, "project: nfields out of range");
     int ntb, lblocks;
     project_lblocks(lpad, &ntb, &lblocks);
     ProjMaps maps;
-    for (int f = 0; f < nfields; f++) {
+    for (int f = 0; f < nmaps; f++) {
         int rc = make_tma_2d(&maps.x[f], x[f], (uint64_t)ncol, (uint64_t)rows, ld_x * sizeof(double), TILE_K, PROJ_BM);
         if (rc) return rc;
     }
-    for (int f = nfields; f < TEMD_MAX_FIELDS; f++) maps.x[f] = maps.x[0];
+    for (int f = nmaps; f < TEMD_MAX_FIELDS; f++) maps.x[f] = maps.x[0];
     int rc = make_tma_2d(&maps.q, qt, (uint64_t)ncol, (uint64_t)lpad, ld_q * sizeof(double), TILE_K, ntb * 8);
     if (rc) return rc;
     ProjParams p;
@@ -245,13 +259,26 @@ int launch_project(const double* const* x, int nfields, int rows, int ncol, size
     p.lpad = lpad;
     p.part = part;
     switch (ntb) {
-#define CASE(N) case N: rc = launch_project_t<N>(maps, p, lblocks, stream); break;
+#define CASE(N) case N: rc = launch_project_t<N>(maps, p, lblocks, prod, stream); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
 #undef CASE
         default: return temd_set_error(-1, "project: bad l-block size");
     }
     if (rc) return temd_set_error(rc, "project: kernel launch failed");
     return launch_reduce_partials(part, out, nsplit, nfields, rows, lpad, lev_scale, scale_field, nlev, stream);
+}
+
+int launch_project(const double* const* x, int nfields, int rows, int ncol, size_t ld_x, const double* qt,
+                   int lpad, size_t ld_q, double* out, double* part, int nsplit, const double* lev_scale,
+                   int scale_field, int nlev, cudaStream_t stream) {
+    return launch_project_impl(x, nfields, false, rows, ncol, ld_x, qt, lpad, ld_q, out, part, nsplit, lev_scale, scale_field,
+                               nlev, stream);
+}
+
+// out[f][row][l] = sum_n x[2f][row][n] x[2f+1][row][n] QT[l][n],  f < npairs (<= 4)
+int launch_project_products(const double* const* xpairs, int npairs, int rows, int ncol, size_t ld_x, const double* qt,
+                            int lpad, size_t ld_q, double* out, double* part, int nsplit, cudaStream_t stream) {
+    return launch_project_impl(xpairs, npairs, true, rows, ncol, ld_x, qt, lpad, ld_q, out, part, nsplit, nullptr, -1, 1, stream);
 }
 
 }  // namespace temd

@@ -8,6 +8,12 @@
 // Classic 128 x 64 x 16 tiling: both operands arrive as 128-B-swizzled TMA boxes (C rows are
 // K-major, B rows are "MN-major"); the contraction index inside a 16-wide block is visited in the
 // order k(t, s) = {0,3,12,15}[t] ^ 2s which makes BOTH fragment loads bank-conflict-free.
+// The contraction is short (lpad / 16 = 7 .. 64 blocks), so a CTA's prologue (barrier set-up, first TMA round trip)
+// and epilogue (64 KB of stores) are not negligible: 4 pipeline stages (96 KB) let TWO CTAs share an SM, one
+// computing while the other starts or drains.
+//
+// Fused eddy epilogue (field = blockIdx.x / row tiles): out_f = lev_scale * X_f - C_f B, i.e. the native-grid eddy field
+// X' = X - ZM.sph_zonal_mean_native(X) of tem_diagnostics.py:517-529 without a separate element-wise pass.
 #include "temd_common.cuh"
 #include "temd_internal.h"
 
@@ -17,21 +23,37 @@ constexpr int SY_BM = 128, SY_BN = 64, SY_BK = 16;
 constexpr int SY_WARPS = 8;
 constexpr int SY_THREADS = (SY_WARPS + 1) * 32;
 constexpr int SY_STAGE_BYTES = SY_BM * TILE_ROW_BYTES + (SY_BN / 16) * SY_BK * TILE_ROW_BYTES;  // 16 KB + 8 KB
-constexpr int SY_STAGES = 8;
+constexpr int SY_STAGES = 4;
 
 struct SynthMaps {
     CUtensorMap c;   // dims {lpad, rows},  box {16, 128}
     CUtensorMap b;   // dims {ncol, lpad},  box {16, 16}
 };
 
-__global__ void __launch_bounds__(SY_THREADS, 1)
-k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, double* __restrict__ out, size_t ld_out) {
+// eddy epilogue of field f (x[f] == nullptr: plain synthesis into out[f])
+struct SynthEpi {
+    const double* x[4];
+    double* out[4];
+    size_t ld_x;
+    const double* lev_scale;   // applied to field `scale_field` only (theta = lev_scale * T)
+    int scale_field, nlev;
+    int c_field_rows;          // row offset between consecutive fields in the coefficient map
+    int row_base;              // first row of this batch inside a field (coefficient rows, lev_scale index)
+};
+
+__global__ void __launch_bounds__(SY_THREADS, 2)
+k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, const SynthEpi epi, size_t ld_out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bars[2 * SY_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * SY_BM;
+    // grid.x = row tiles x fields (fastest): the CTAs that share a B (basis) column tile run back to back, so the
+    // basis is read from HBM once per launch and served from L2 to every row tile and field
+    const int row_tiles = (rows + SY_BM - 1) / SY_BM;
+    const int row0 = (blockIdx.x % row_tiles) * SY_BM;
     const int col0 = blockIdx.y * SY_BN;
+    const int fld = blockIdx.x / row_tiles;
+    const int crow0 = fld * epi.c_field_rows + epi.row_base + row0;   // row coordinate in the coefficient map
     const uint32_t smem_base = smem_u32(smem), bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (SY_STAGES + s); };
@@ -50,7 +72,7 @@ k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, dou
                 mbar_wait(empty_bar(s), ((i / SY_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(full_bar(s), SY_STAGE_BYTES);
                 const uint32_t dst = smem_base + s * SY_STAGE_BYTES;
-                tma_load_2d(dst, &maps.c, i * SY_BK, row0, full_bar(s));
+                tma_load_2d(dst, &maps.c, i * SY_BK, crow0, full_bar(s));
 #pragma unroll
                 for (int b = 0; b < SY_BN / 16; b++)
                     tma_load_2d(dst + SY_BM * TILE_ROW_BYTES + b * SY_BK * TILE_ROW_BYTES, &maps.b, col0 + b * 16,
@@ -103,38 +125,78 @@ k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, dou
         if (lane == 0) mbar_arrive(empty_bar(s));
     }
 
+    // explicit selects: indexing a kernel-parameter array with a run-time index would copy it to local memory
+    double* __restrict__ out = fld == 0 ? epi.out[0] : fld == 1 ? epi.out[1] : fld == 2 ? epi.out[2] : epi.out[3];
+    const double* __restrict__ xin = fld == 0 ? epi.x[0] : fld == 1 ? epi.x[1] : fld == 2 ? epi.x[2] : epi.x[3];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
         const int row = row0 + wm * 32 + mi * 8 + g;
         if (row >= rows) continue;
+        double sc = 1.0;
+        if (xin != nullptr && epi.lev_scale != nullptr && fld == epi.scale_field) sc = epi.lev_scale[(epi.row_base + row) % epi.nlev];
 #pragma unroll
         for (int jn = 0; jn < 4; jn++) {
             const int col = col0 + wn * 32 + jn * 8 + 2 * t;
             double* dst = out + (size_t)row * ld_out + col;
-            if (col + 1 < ncol) *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][jn][0], acc[mi][jn][1]);
-            else if (col < ncol) *dst = acc[mi][jn][0];
+            double v0 = acc[mi][jn][0], v1 = acc[mi][jn][1];
+            if (xin != nullptr) {
+                const double* xs = xin + (size_t)row * epi.ld_x + col;
+                if (col + 1 < ncol) { const double2 x2 = *reinterpret_cast<const double2*>(xs); v0 = sc * x2.x - v0; v1 = sc * x2.y - v1; }
+                else if (col < ncol) v0 = sc * xs[0] - v0;
+            }
+            if (col + 1 < ncol) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            else if (col < ncol) *dst = v0;
         }
     }
 }
 
-int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b, double* out,
-                 size_t ld_out, cudaStream_t stream) {
+static int launch_synth_impl(const double* c, int c_rows_total, int rows, int lpad, size_t ld_c, const double* b, int ncol,
+                             size_t ld_b, const SynthEpi& epi, int nfields, size_t ld_out, cudaStream_t stream) {
     SynthMaps maps;
-    int rc = make_tma_2d(&maps.c, c, (uint64_t)lpad, (uint64_t)rows, ld_c * sizeof(double), SY_BK, SY_BM);
+    int rc = make_tma_2d(&maps.c, c, (uint64_t)lpad, (uint64_t)c_rows_total, ld_c * sizeof(double), SY_BK, SY_BM);
     if (rc) return rc;
     rc = make_tma_2d(&maps.b, b, (uint64_t)ncol, (uint64_t)lpad, ld_b * sizeof(double), 16, SY_BK);
     if (rc) return rc;
-    if ((ld_out & 1) || (reinterpret_cast<uintptr_t>(out) & 15)) return temd_set_error(-1, "synth: output must be 16-byte aligned with an even leading dimension");
+    for (int f = 0; f < nfields; f++)
+        if ((ld_out & 1) || (reinterpret_cast<uintptr_t>(epi.out[f]) & 15))
+            return temd_set_error(-1, "synth: output must be 16-byte aligned with an even leading dimension");
     constexpr int smem = SY_STAGES * SY_STAGE_BYTES + 1024;
     // per-device attribute: set on every launch (cheap) so that several devices in one process all work
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return temd_set_error((int)e, "synth: cudaFuncSetAttribute failed");
-    dim3 grid((rows + SY_BM - 1) / SY_BM, (ncol + SY_BN - 1) / SY_BN);
+    const int col_tiles = (ncol + SY_BN - 1) / SY_BN;
+    if (col_tiles > 65535) return temd_set_error(-1, "synth: too many column tiles");
+    dim3 grid(((rows + SY_BM - 1) / SY_BM) * nfields, col_tiles);
     const int nkb = (lpad + SY_BK - 1) / SY_BK;
-    k_synth<<<grid, SY_THREADS, smem, stream>>>(maps, rows, ncol, nkb, out, ld_out);
+    k_synth<<<grid, SY_THREADS, smem, stream>>>(maps, rows, ncol, nkb, epi, ld_out);
     rc = (int)cudaGetLastError();
     if (rc) return temd_set_error(rc, "synth: kernel launch failed");
     return 0;
+}
+
+int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b, double* out,
+                 size_t ld_out, cudaStream_t stream) {
+    SynthEpi epi = {};
+    epi.out[0] = out;
+    epi.scale_field = -1;
+    epi.nlev = 1;
+    return launch_synth_impl(c, rows, rows, lpad, ld_c, b, ncol, ld_b, epi, 1, ld_out, stream);
+}
+
+// Eddy fields of a row batch: out[f][r][n] = lev_scale * x[f][r0 + r][n] - (C_f B)[r0 + r][n], r < rows, f < 4
+// (coef4 is [4][rows_total][lpad]; x[f] / out[f] point at the batch's first row).
+int launch_synth_eddy4(const double* coef4, int rows_total, int r0, int rows, int lpad, const double* b, int ncol, size_t ld_b,
+                       const double* const* x, size_t ld_x, const double* lev_scale, int nlev, double* const* out,
+                       size_t ld_out, cudaStream_t stream) {
+    SynthEpi epi = {};
+    for (int f = 0; f < 4; f++) { epi.x[f] = x[f]; epi.out[f] = out[f]; }
+    epi.ld_x = ld_x;
+    epi.lev_scale = lev_scale;
+    epi.scale_field = 2;
+    epi.nlev = nlev < 1 ? 1 : nlev;
+    epi.c_field_rows = rows_total;
+    epi.row_base = r0;
+    return launch_synth_impl(coef4, 4 * rows_total, rows, lpad, (size_t)lpad, b, ncol, ld_b, epi, 4, ld_out, stream);
 }
 
 }  // namespace temd

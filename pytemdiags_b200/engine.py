@@ -214,18 +214,9 @@ class Engine:
         """xs = (u, v, T, omega) as [rows][N] device tensors -> ([4][rows][lpad] coefficients of ub, vb, thetab, wapb,
         [3][rows][lpad] coefficients of upvpb, upwappb, vptpb)."""
         c4 = self.project(list(xs[:4]), lev_scale=lev_scale, scale_field=2, nlev=nlev)
-        if self.lpad <= 408:
-            return c4, self.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, nlev)
-        # L + 1 > 408: the coefficient tile of the fused kernel no longer fits in shared memory.  Staged GPU path:
-        # native means -> eddies -> products -> projections (eddies ARE materialised, a slab at a time).
-        eu = self.eddy_native(xs[0], c4[0])
-        ev = self.eddy_native(xs[1], c4[1])
-        ew = self.eddy_native(xs[3], c4[3])
-        prods = [self.multiply(eu, ev), self.multiply(eu, ew)]
-        et = self.eddy_native(xs[2], c4[2], lev_scale, nlev)
-        prods.append(self.multiply(ev, et))
-        del et, eu, ev, ew
-        return c4, self.project(prods)
+        # libtemd picks the implementation: the fully fused kernel for L + 1 <= 104, the split synth-eddy /
+        # product-projection pipeline above that (eddies go through a bounded scratch buffer, a row batch at a time)
+        return c4, self.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, nlev)
 
     def tracer_coefficients(self, qs, xs, c4, lev_scale, nlev):
         """Tracer TEM inputs (tem_diagnostics.py:532-538,560-570).  qs: list of [rows][N] tracers; xs, c4 as in
@@ -235,17 +226,10 @@ class Engine:
         rows = xs[0].shape[0]
         out = torch.empty((3 * len(qs), rows, self.lpad), dtype=torch.float64, device=self.device)
         cq_all = torch.cat([self.project(list(qs[i:i + 8])) for i in range(0, len(qs), 8)], 0)
-        ev = ew = None
         for i, q in enumerate(qs):
             out[3 * i] = cq_all[i]
-            if self.lpad <= 408:
-                c4q = torch.cat([cq_all[i:i + 1], c4[1:]], 0)
-                out[3 * i + 1:3 * i + 3] = self.eddy_flux_project(q, xs[1], xs[2], xs[3], c4q, lev_scale, nlev)[:2]
-            else:
-                if ev is None:
-                    ev, ew = self.eddy_native(xs[1], c4[1]), self.eddy_native(xs[3], c4[3])
-                eq = self.eddy_native(q, cq_all[i])
-                out[3 * i + 1:3 * i + 3] = self.project([self.multiply(eq, ev), self.multiply(eq, ew)])
+            c4q = torch.cat([cq_all[i:i + 1], c4[1:]], 0)
+            out[3 * i + 1:3 * i + 3] = self.eddy_flux_project(q, xs[1], xs[2], xs[3], c4q, lev_scale, nlev)[:2]
         return out
 
     def tem_epilogue(self, zm, p_pa, f, coslat, p0=P0):

@@ -433,14 +433,10 @@ class TEMDiagnostics:
         nf = len(names)
         ld = N + (N & 1)
         zero_copy = all(self._is_native_device_layout(v, dev) for v in names)
-        fused = eng.lpad <= 408 or self._dedup
         # slab size: in-place device inputs need no staging, so the whole record goes in one launch (best wave
         # quantisation); host inputs stream through two ~2 GB staging sets
-        budget = self._slab_bytes if self._slab_bytes is not None else (
-            ((1 << 42) if fused else (16 << 30)) if zero_copy else (2 << 30))
+        budget = self._slab_bytes if self._slab_bytes is not None else ((1 << 42) if zero_copy else (2 << 30))
         ts = max(1, min(T, int(budget // (nf * 8 * K * N))))
-        if not fused:
-            ts = max(1, ts // 3)      # the staged path keeps 3 eddies + 3 products of a slab resident
         coef = torch.empty((7, T * K, eng.lpad), dtype=torch.float64, device=dev)
         coefq = torch.empty((3 * ntr, T * K, eng.lpad), dtype=torch.float64, device=dev) if ntr else None
 

@@ -68,5 +68,48 @@ def test_fused_path_variants(ne, K, T, L):
 def test_eddy_warp_layouts(monkeypatch, warps):
     """both consumer-warp layouts of k_eddy (the default is 16 for BM >= 16)"""
     monkeypatch.setenv('TEMD_EDDY_WARPS', warps)
+    monkeypatch.setenv('TEMD_EDDY_MODE', 'fused')
     test_fused_path_variants(8, 11, 3, 62)
     test_fused_path_variants(20, 7, 3, 130)
+
+
+@pytest.mark.parametrize('mode', ['fused', 'split'])
+def test_eddy_implementations(monkeypatch, mode):
+    """temd_eddy_flux_project has two implementations (fused k_eddy: default for L + 1 <= 104; split k_synth eddy
+    epilogue + k_project product mode: default above).  Force each one across the L range both can serve, including
+    the fused kernel's BM = 16 / 8 variants that the default no longer selects, ragged row batches (scratch budget of
+    one 128-row batch) and the product-mode projection with several l-blocks."""
+    monkeypatch.setenv('TEMD_EDDY_MODE', mode)
+    monkeypatch.setenv('TEMD_EDDY_SCRATCH_GB', '1e-6')          # split: 128-row batches -> several batches, last one ragged
+    for case in ((4, 7, 3, 8), (6, 9, 5, 33), (12, 6, 5, 103), (20, 5, 3, 104), (16, 50, 3, 130), (32, 3, 3, 207),
+                 (32, 5, 1, 210), (32, 3, 2, 250)):
+        test_fused_path_variants(*case)
+
+
+def test_split_and_fused_agree_closely():
+    """Same contraction, different kernels: the flux coefficients agree to ~1e-13 of their magnitude."""
+    import os
+    import torch
+    from pytemdiags_b200.engine import Engine
+    lat, lon = syn.pg2_grid(16)
+    K, T, L = 40, 4, 150
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=77)
+    eng = Engine(lat, oracle.zm_latitudes(1), L).build_basis()
+    C = oracle.CONSTANTS
+    sc = torch.as_tensor((C['P0'] / (plev * 100)) ** C['k']).cuda()
+    xs = [torch.as_tensor(f[n].reshape(T * K, -1)).cuda() for n in ('ua', 'va', 'ta', 'wap')]
+    c4 = eng.project(xs, lev_scale=sc, scale_field=2, nlev=K)
+    out = {}
+    old = os.environ.get('TEMD_EDDY_MODE')
+    try:
+        for mode in ('fused', 'split'):
+            os.environ['TEMD_EDDY_MODE'] = mode
+            out[mode] = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, sc, K)
+    finally:
+        if old is None:
+            os.environ.pop('TEMD_EDDY_MODE', None)
+        else:
+            os.environ['TEMD_EDDY_MODE'] = old
+    for q in range(3):
+        assert nerr(out['split'][q].cpu().numpy(), out['fused'][q].cpu().numpy()) < 1e-11
