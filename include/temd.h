@@ -168,10 +168,11 @@ int temd_basis_build_dedup(temd_plan* plan, const double* x_unique, const double
  * lev_scale/scale_field as in temd_project turn T into theta): TEMD_GS_NPLANES planes [row][ld_out]:
  *   0-3 a0_f (first member of the group), 4-7 s_f = sum (x_f - a0_f), 8-10 sum (x_a - a0_a)(x_b - a0_b) for
  *   (a,b) = (u,v), (u,omega), (v,theta), 11-14 the weighted sums of with_products = 0.
- * max_count / min_count: largest / smallest multiplicity (selects the warp-per-group and thread-per-group kernels). */
+ * max_count / min_count: largest / smallest multiplicity (selects the warp-per-group and thread-per-group kernels);
+ * even_groups != 0: every goff[] entry is even (with perm == NULL this allows 16-byte loads). */
 #define TEMD_GS_NPLANES 15
 int temd_group_sums(const double* const* fields_host, int nfields, int rows, size_t ld, const int* perm,
-                    const int* goff, int ngroups, int max_count, int min_count, const double* rsq,
+                    const int* goff, int ngroups, int max_count, int min_count, int even_groups, const double* rsq,
                     const double* lev_scale, int scale_field, int nlev, int with_products, double* out,
                     size_t ld_out, void* stream);
 

@@ -93,7 +93,7 @@ def load():
     lib.temd_host_copy.argtypes = [vp, vp, sz, i]
     lib.temd_synth_fields.argtypes = [vp, i, i, i, i, i, i, sz, vp, vp, vp, vp]
     lib.temd_basis_build_dedup.argtypes = [vp, vp, vp, vp, C.POINTER(d), vp]
-    lib.temd_group_sums.argtypes = [C.POINTER(vp), i, i, sz, vp, vp, i, i, i, vp, vp, i, i, i, vp, sz, vp]
+    lib.temd_group_sums.argtypes = [C.POINTER(vp), i, i, sz, vp, vp, i, i, i, i, vp, vp, i, i, i, vp, sz, vp]
     lib.temd_dedup_flux.argtypes = [vp, sz, vp, sz, vp, vp, i, i, vp, sz, vp]
     lib.temd_dedup_expand.argtypes = [vp, sz, vp, i, vp, sz, vp, vp, d, d, vp, sz, i, i, vp]
     lib.temd_comm_unique_id.argtypes = [C.c_char_p]

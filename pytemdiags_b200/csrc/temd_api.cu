@@ -637,7 +637,7 @@ extern "C" int temd_tracer_epilogue(temd_plan* p, const temd_tracer_args* args, 
 
 namespace temd {
 int launch_group_sums(const double* const* x, int nfields, int rows, size_t ld, const int* perm, const int* goff,
-                      int ngroups, int max_count, int min_count, const double* rsq, const double* lev_scale,
+                      int ngroups, int max_count, int min_count, int even_groups, const double* rsq, const double* lev_scale,
                       int scale_field, int nlev, int with_products, double* out, size_t ld_out, cudaStream_t stream);
 int launch_dedup_flux(const double* gs, size_t ld_gs, const double* mw, size_t ld_m, const int* goff, const double* rsq,
                       int rows, int ngroups, double* out, size_t ld_o, cudaStream_t stream);
@@ -647,7 +647,7 @@ int launch_dedup_expand(const double* x, size_t ld_x, const double* scale, int n
 }
 
 extern "C" int temd_group_sums(const double* const* fields_host, int nfields, int rows, size_t ld, const int* perm,
-                               const int* goff, int ngroups, int max_count, int min_count, const double* rsq,
+                               const int* goff, int ngroups, int max_count, int min_count, int even_groups, const double* rsq,
                                const double* lev_scale, int scale_field, int nlev, int with_products, double* out,
                                size_t ld_out, void* stream) {
     if (!fields_host || !goff || !rsq || !out || nfields < 1 || nfields > 4 || rows < 1 || ngroups < 1 ||
@@ -655,7 +655,7 @@ extern "C" int temd_group_sums(const double* const* fields_host, int nfields, in
         return temd_set_error(-1, "group_sums: bad arguments");
     if (with_products && nfields != 4) return temd_set_error(-1, "group_sums: the flux sums need the four fields u, v, T, omega");
     for (int f = 0; f < nfields; f++) if (!fields_host[f]) return temd_set_error(-1, "group_sums: null field");
-    const int rc = launch_group_sums(fields_host, nfields, rows, ld, perm, goff, ngroups, max_count, min_count, rsq, lev_scale,
+    const int rc = launch_group_sums(fields_host, nfields, rows, ld, perm, goff, ngroups, max_count, min_count, even_groups, rsq, lev_scale,
                                      lev_scale ? scale_field : -1, nlev, with_products, out, ld_out,
                                      reinterpret_cast<cudaStream_t>(stream));
     if (rc) return temd_set_error(rc, "group_sums: kernel launch failed");

@@ -325,6 +325,7 @@ class DedupEngine(Engine):
         goff = np.concatenate([[0], np.cumsum(cnt)])
         self._xu = xu
         self._cnt_minmax = (int(cnt.min()), int(cnt.max()))
+        self._even_groups = int(bool(np.all(goff % 2 == 0)))
         i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
         self._perm = None if perm is None else i32(perm)
         self._goff, self._gid = i32(goff), i32(inv)
@@ -367,7 +368,7 @@ class DedupEngine(Engine):
         ptrs = (C.c_void_p * len(fields))(*[x.data_ptr() for x in fields])
         with torch.cuda.device(self.device):
             rc = self.lib.temd_group_sums(ptrs, len(fields), rows, ld, _ptr(self._perm), _ptr(self._goff), self.NU,
-                                          self._cnt_minmax[1], self._cnt_minmax[0], _ptr(self._rsq), _ptr(lev_scale),
+                                          self._cnt_minmax[1], self._cnt_minmax[0], self._even_groups, _ptr(self._rsq), _ptr(lev_scale),
                                           scale_field, nlev, int(with_products), _ptr(out), self.Uld, self.stream)
         _lib.check(rc, 'temd_group_sums')
         return out

@@ -35,10 +35,12 @@ def _grids():
     order = rng.permutation(lat_mix.shape[0])
     lat_mix = lat_mix[order]
     lon_mix = rng.uniform(0, 360, lat_mix.shape[0])
-    return {'latlon': (lat_ll, lon_ll, 14), 'pg2': (lat_pg, lon_pg, 20), 'mixed': (lat_mix, lon_mix, 16)}
+    lat_lo, lon_lo = syn.latlon_grid(20, 45, poles=False)       # contiguous groups at ODD offsets: scalar-load mode
+    return {'latlon': (lat_ll, lon_ll, 14), 'latlon_odd': (lat_lo, lon_lo, 12), 'pg2': (lat_pg, lon_pg, 20),
+            'mixed': (lat_mix, lon_mix, 16)}
 
 
-@pytest.mark.parametrize('grid', ['latlon', 'pg2', 'mixed'])
+@pytest.mark.parametrize('grid', ['latlon', 'latlon_odd', 'pg2', 'mixed'])
 def test_dedup_matches_dense_and_oracle(grid):
     from pytemdiags_b200 import TEMDiagnostics
     lat, lon, L = _grids()[grid]
@@ -141,7 +143,7 @@ def test_group_sums_c_abi_against_numpy(temd_lib):
     dperm, dgoff, drsq, dsc = d(perm, np.int32), d(goff, np.int32), d(1 / np.sqrt(cnt)), d(sc)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     rc = temd_lib.temd_group_sums(ptrs, 4, rows, N, C.c_void_p(dperm.data_ptr()), C.c_void_p(dgoff.data_ptr()), U,
-                                  int(cnt.max()), int(cnt.min()), C.c_void_p(drsq.data_ptr()), C.c_void_p(dsc.data_ptr()),
+                                  int(cnt.max()), int(cnt.min()), 0, C.c_void_p(drsq.data_ptr()), C.c_void_p(dsc.data_ptr()),
                                   2, nlev, 1, C.c_void_p(out.data_ptr()), Uld, st)
     assert rc == 0, temd_lib.temd_last_error()
     got = out.cpu().numpy()[:, :, :U]
@@ -162,7 +164,7 @@ def test_group_sums_c_abi_against_numpy(temd_lib):
     out3 = torch.zeros_like(out2)
     for o in (out2, out3):
         rc = temd_lib.temd_group_sums(ptrs, 2, rows, N, C.c_void_p(dperm.data_ptr()), C.c_void_p(dgoff.data_ptr()), U,
-                                      int(cnt.max()), int(cnt.min()), C.c_void_p(drsq.data_ptr()), None, -1, 1, 0,
+                                      int(cnt.max()), int(cnt.min()), 0, C.c_void_p(drsq.data_ptr()), None, -1, 1, 0,
                                       C.c_void_p(o.data_ptr()), Uld, st)
         assert rc == 0
     assert torch.equal(out2, out3)

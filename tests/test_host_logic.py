@@ -127,3 +127,33 @@ def test_format_latlon_data_column_order():
     assert np.array_equal(B2, A2)
     with pytest.raises(RuntimeError):
         format_latlon_data(A, lat[:-1], lon)
+
+
+def test_format_latlon_data_reference_signature():
+    """Dataset in, Dataset out, as tem_util.py:247-342 (a mapping name -> (dims, array) stands in for xarray.Dataset):
+    (lat, lon) stacked lat-major into a leading 'ncol', lat / lon kept as ('ncol',) variables, bounds variables added."""
+    from pytemdiags_b200.util import format_latlon_data
+    import PyTEMDiags
+    lat = np.linspace(-90, 90, 5)
+    lon = np.arange(8) * 45.0
+    A = np.arange(3 * 5 * 8, dtype=np.float64).reshape(3, 5, 8)
+    ds = {'ua': (('time', 'lat', 'lon'), A), 'ps': (('lat', 'lon'), A[0]), 'hyam': (('lev',), np.arange(4.0)),
+          'lat': (('lat',), lat), 'lon': (('lon',), lon)}
+    out = format_latlon_data(ds)
+    assert out['ua'][0] == ('ncol', 'time') and out['ua'][1].shape == (40, 3)
+    assert out['ua'][1][2 * 8 + 3, 1] == A[1, 2, 3]                     # ncol = ilat * NLON + ilon (:331)
+    assert out['ps'][0] == ('ncol',) and np.array_equal(out['ps'][1], A[0].ravel())
+    assert out['hyam'][0] == ('lev',)                                     # variables without lat/lon pass through
+    glat, glon = syn.latlon_grid(5, 8)
+    assert out['lat'][0] == ('ncol',) and np.array_equal(out['lat'][1], glat) and np.array_equal(out['lon'][1], glon)
+    # bounds at the midpoints between neighbours (:309-323), stacked like every other (lat)/(lon) variable
+    assert out['lat_bnds'][0] == ('ncol', 'nbnd') and out['lat_bnds'][1].shape == (40, 2)
+    assert np.allclose(out['lat_bnds'][1][8], [-67.5, -22.5]) and np.allclose(out['lon_bnds'][1][3], [112.5, 157.5])
+    # custom names, existing bounds with a wrong bound-dimension name -> the reference's RuntimeError
+    ds2 = {'t': (('latitude', 'longitude'), A[0]), 'latitude': (('latitude',), lat), 'longitude': (('longitude',), lon),
+           'lat_bnds': (('latitude', 'bnds'), np.zeros((5, 2)))}
+    with pytest.raises(RuntimeError, match='does not have dimension'):
+        format_latlon_data(ds2, 'latitude', 'longitude')
+    out2 = format_latlon_data(ds2, lat_name='latitude', lon_name='longitude', bnddim_name='bnds')
+    assert out2['t'][0] == ('ncol',)
+    assert hasattr(PyTEMDiags, 'tem_util') and PyTEMDiags.tem_util.format_latlon_data is format_latlon_data
