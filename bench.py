@@ -531,6 +531,8 @@ def run_record(ctx, cfgname, sub_steps, dedup=False):
     if starts:                       # warm-up: first slab + tail (allocations, attribute calls, NCCL channel set-up)
         slab(starts[0], min(b, starts[0] + sub_steps))
     tail()
+    tail()       # twice: the engine keeps the last epilogue planes alive, so only the third call finds a cached block
+                 # (a fresh cudaMalloc of ~100 MB costs tens of ms once NCCL has enabled peer access)
     ev.clear()
     ctx.barrier()
     for s0 in starts:

@@ -61,6 +61,13 @@ int temd_project(temd_plan* plan, const double* const* fields_host, int nfields,
 /* sph_zonal_mean (sph_zonal_mean.py:291-296): out[row][m] on the output latitudes, ld_out >= M, even. */
 int temd_synth_out(temd_plan* plan, const double* coef, int rows, double* out, size_t ld_out, void* stream);
 
+/* Optional Legendre-space latitude derivative (BASELINE.json north_star; NOT used by the reference, whose
+ * lat_gradient is a finite difference, tem_util.py:154): out[row][m] = d/dphi of the zonal mean of sph_zonal_mean at the
+ * output latitudes, per radian, = sum_l b_l dY_l/dphi(phi_m) with dY_l/dphi = cos(phi) Y_l'(sin phi) from the
+ * differentiated three-term recurrence.  temd_basis_export_dlat writes the dense dY0p [M][L+1]. */
+int temd_synth_out_dlat(temd_plan* plan, const double* coef, int rows, double* out, size_t ld_out, void* stream);
+int temd_basis_export_dlat(temd_plan* plan, double* dY0p, void* stream);
+
 /* sph_zonal_mean_native (sph_zonal_mean.py:285-290): out[row][n] on the native columns. */
 int temd_synth_native(temd_plan* plan, const double* coef, int rows, double* out, size_t ld_out, void* stream);
 

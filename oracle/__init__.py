@@ -13,6 +13,6 @@ against outputs of the UNMODIFIED reference source executed in the build contain
 analytic known-answer checks of the reference's `tests_sph_zonal_mean.py:297-477`.
 """
 from .tem_oracle import (  # noqa: F401
-    CONSTANTS, zm_latitudes, sph_basis, sph_basis_recurrence, sph_matrices,
+    CONSTANTS, zm_latitudes, sph_basis, sph_basis_dlat, sph_basis_recurrence, sph_matrices,
     zonal_mean, tem_suite, TEM_OUTPUTS, TEM_INTERMEDIATES,
 )

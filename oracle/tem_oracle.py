@@ -56,6 +56,29 @@ def sph_basis_recurrence(x, L):
     return Y
 
 
+def sph_basis_dlat(lat_deg, L):
+    """d/dphi of the basis of `sph_basis` (phi = latitude in radians), (N, L+1): cos(phi) * d/dx [N_l P_l(x)], x = sin(phi),
+    by the differentiated three-term recurrence.  NO reference counterpart: the reference differentiates by
+    np.gradient (tem_util.py:154); this restates the optional Legendre-space derivative named by BASELINE.json's
+    north_star and is pinned against mpmath in tests/test_oracle_golden.py."""
+    x = np.cos(np.deg2rad(90 - np.asarray(lat_deg, dtype=np.float64)))
+    c = np.sqrt(np.maximum(0.0, (1.0 - x) * (1.0 + x)))
+    n = x.shape[0]
+    Y = np.zeros((n, L + 1))
+    D = np.zeros((n, L + 1))
+    Y[:, 0] = np.sqrt(1.0 / (4.0 * np.pi))
+    if L >= 1:
+        a1 = np.sqrt(3.0 / (4.0 * np.pi))
+        Y[:, 1] = a1 * x
+        D[:, 1] = a1
+    for l in range(2, L + 1):
+        a = np.sqrt(4.0 * l * l - 1.0) / l
+        b = ((l - 1.0) / l) * np.sqrt((2.0 * l + 1.0) / (2.0 * l - 3.0))
+        Y[:, l] = a * x * Y[:, l - 1] - b * Y[:, l - 2]
+        D[:, l] = a * (Y[:, l - 1] + x * D[:, l - 1]) - b * D[:, l - 2]
+    return D * c[:, None]
+
+
 def sph_basis(lat_deg, L):
     """sph_zonal_mean.py:359-363 — Y0[:,l] = sph_harm(0, l, 0, coalt).real, coalt = deg2rad(90-lat).
 

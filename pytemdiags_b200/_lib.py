@@ -14,7 +14,7 @@ SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
     'temd_basis_build', 'temd_basis_build_weighted', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
     'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_host_copy', 'temd_synth_fields',
-    'temd_basis_build_dedup', 'temd_group_sums', 'temd_dedup_flux', 'temd_dedup_expand',
+    'temd_synth_out_dlat', 'temd_basis_export_dlat', 'temd_basis_build_dedup', 'temd_group_sums', 'temd_dedup_flux', 'temd_dedup_expand',
     'temd_comm_unique_id', 'temd_comm_init', 'temd_comm_destroy', 'temd_allgather_outputs',
 )
 
@@ -84,6 +84,8 @@ def load():
     lib.temd_project.argtypes = [vp, C.POINTER(vp), i, i, sz, vp, i, i, vp, vp]
     lib.temd_synth_out.argtypes = [vp, vp, i, vp, sz, vp]
     lib.temd_synth_native.argtypes = [vp, vp, i, vp, sz, vp]
+    lib.temd_synth_out_dlat.argtypes = [vp, vp, i, vp, sz, vp]
+    lib.temd_basis_export_dlat.argtypes = [vp, vp, vp]
     lib.temd_eddy_native.argtypes = [vp, vp, sz, vp, i, vp, i, vp, sz, vp]
     lib.temd_multiply.argtypes = [vp, sz, vp, sz, vp, sz, i, i, vp]
     lib.temd_eddy_flux_project.argtypes = [vp, vp, vp, vp, vp, i, sz, vp, vp, i, vp, vp]

@@ -183,6 +183,8 @@ struct temd_plan {
     size_t ld_q, ld_p;
     double *qt, *qt_alt;     // whitened basis Q^T [lpad][ld_q] and ping-pong buffer
     double *qpt, *qpt_alt;   // whitened output-grid basis [lpad][ld_p]
+    double *dqpt;            // whitened latitude-derivative basis on the output grid (lazy, temd_synth_out_dlat)
+    bool dqpt_built;
     double *linv, *linv1, *linv2, *gram, *lt;   // [lpad][lpad] each
     double *rec_a, *rec_b;   // recurrence coefficients [L+1]
     double *x, *x_out;       // copies of the node coordinates (for exports)
@@ -255,7 +257,7 @@ extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_
 extern "C" int temd_plan_destroy(temd_plan* p) {
     if (p == nullptr) return 0;
     DeviceGuard guard(p->dev);
-    double* bufs[] = {p->qt, p->qt_alt, p->qpt, p->qpt_alt, p->linv, p->linv1, p->linv2, p->gram, p->lt,
+    double* bufs[] = {p->dqpt, p->qt, p->qt_alt, p->qpt, p->qpt_alt, p->linv, p->linv1, p->linv2, p->gram, p->lt,
                       p->rec_a, p->rec_b, p->x, p->x_out, p->sanity};
     for (double* b : bufs) if (b) cudaFree(b);
     if (p->work) for (auto& kv : *p->work) if (kv.second.first) cudaFree(kv.second.first);
@@ -365,6 +367,7 @@ static int basis_build_impl(temd_plan* p, const double* x, const double* x_out, 
     TEMD_CUDA(cudaStreamSynchronize(st));
     p->built = true;
     p->weighted = false;
+    p->dqpt_built = false;
     return 0;
 }
 
@@ -404,6 +407,7 @@ extern "C" int temd_basis_build_weighted(temd_plan* p, const double* x, const do
     TEMD_CUDA(cudaStreamSynchronize(st));
     p->built = true;
     p->weighted = true;
+    p->dqpt_built = false;
     return 0;
 }
 
@@ -475,6 +479,40 @@ extern "C" int temd_synth_out(temd_plan* p, const double* coef, int rows, double
     if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->M) return temd_set_error(-1, "synth_out: bad arguments");
     TEMD_ON_DEVICE(p->dev);
     return launch_synth(coef, rows, p->lpad, p->lpad, p->qpt, p->M, p->ld_p, out, ld_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// whitened derivative basis on the output grid: dQp^T = Linv * dY0p^T (quadrature mode: the raw derivative basis)
+static int ensure_dqpt(temd_plan* p, cudaStream_t st) {
+    if (p->dqpt_built) return 0;
+    if (p->dqpt == nullptr) TEMD_CUDA(cudaMalloc(&p->dqpt, (size_t)p->lpad * p->ld_p * sizeof(double)));
+    int rc;
+    double* raw = p->weighted ? p->dqpt : p->qpt_alt;
+    if ((rc = launch_basis_dlat(p->x_out, p->M, p->L, p->rec_a, p->rec_b, raw, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis_dlat launch failed");
+    if (!p->weighted && (rc = launch_synth(p->linv, p->lpad, p->lpad, p->lpad, raw, p->M, p->ld_p, p->dqpt, p->ld_p, st))) return rc;
+    p->dqpt_built = true;
+    return 0;
+}
+
+extern "C" int temd_synth_out_dlat(temd_plan* p, const double* coef, int rows, double* out, size_t ld_out, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "synth_out_dlat: basis not built");
+    if (coef == nullptr || out == nullptr || rows < 1 || ld_out < (size_t)p->M) return temd_set_error(-1, "synth_out_dlat: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_ON_DEVICE(p->dev);
+    int rc = ensure_dqpt(p, st);
+    if (rc) return rc;
+    return launch_synth(coef, rows, p->lpad, p->lpad, p->dqpt, p->M, p->ld_p, out, ld_out, st);
+}
+
+extern "C" int temd_basis_export_dlat(temd_plan* p, double* dY0p, void* stream) {
+    if (p == nullptr || !p->built || dY0p == nullptr) return temd_set_error(-1, "basis_export_dlat: basis not built / null output");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TEMD_ON_DEVICE(p->dev);
+    int rc;
+    if ((rc = launch_basis_dlat(p->x_out, p->M, p->L, p->rec_a, p->rec_b, p->qpt_alt, p->ld_p, p->lpad, st))) return temd_set_error(rc, "basis_dlat launch failed");
+    dim3 tb(32, 8), grid((p->M + 31) / 32, (p->Lp + 31) / 32);
+    k_transpose<<<grid, tb, 0, st>>>(p->qpt_alt, p->Lp, p->M, p->ld_p, dY0p, p->Lp);
+    TEMD_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int temd_synth_native(temd_plan* p, const double* coef, int rows, double* out, size_t ld_out, void* stream) {

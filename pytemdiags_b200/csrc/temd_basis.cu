@@ -43,6 +43,44 @@ int launch_basis(const double* x, int n, int L, const double* rec_a, const doubl
     return (int)cudaGetLastError();
 }
 
+// Latitude derivative of the basis, D[l][n] = d/dphi [ sqrt((2l+1)/4pi) P_l(sin phi) ] = cos(phi) Y_l'(x), x = sin(phi),
+// from the differentiated recurrence  Y_l' = a_l (Y_{l-1} + x Y_{l-1}') - b_l Y_{l-2}'  (bounded at the poles, where
+// the closed form l (P_{l-1} - x P_l) / cos(phi) is 0/0).  Optional Legendre-space derivative output (BASELINE.json
+// north_star); the reference itself differentiates by finite differences (tem_util.py:154), so nothing on the
+// default path uses it.
+__global__ void k_basis_dlat(const double* __restrict__ x, int n, int L, const double* __restrict__ rec_a,
+                             const double* __restrict__ rec_b, double* __restrict__ dt, size_t ld, int lpad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    if (i >= (size_t)n) {
+        for (int l = 0; l < lpad; l++) dt[(size_t)l * ld + i] = 0.0;
+        return;
+    }
+    const double xi = x[i];
+    const double c = sqrt(fmax(0.0, (1.0 - xi) * (1.0 + xi)));      // cos(phi)
+    double pm2 = rec_a[0], dm2 = 0.0;                               // Y_0, Y_0'
+    dt[i] = 0.0;
+    if (L >= 1) {
+        double pm1 = rec_a[1] * xi, dm1 = rec_a[1];                 // Y_1, Y_1'
+        dt[ld + i] = c * dm1;
+        for (int l = 2; l <= L; l++) {
+            const double p = rec_a[l] * xi * pm1 - rec_b[l] * pm2;
+            const double d = rec_a[l] * (pm1 + xi * dm1) - rec_b[l] * dm2;
+            dt[(size_t)l * ld + i] = c * d;
+            pm2 = pm1; pm1 = p;
+            dm2 = dm1; dm1 = d;
+        }
+    }
+    for (int l = L + 1; l < lpad; l++) dt[(size_t)l * ld + i] = 0.0;
+}
+
+int launch_basis_dlat(const double* x, int n, int L, const double* rec_a, const double* rec_b, double* dt, size_t ld,
+                      int lpad, cudaStream_t stream) {
+    const int threads = 128;
+    k_basis_dlat<<<(unsigned)((ld + threads - 1) / threads), threads, 0, stream>>>(x, n, L, rec_a, rec_b, dt, ld, lpad);
+    return (int)cudaGetLastError();
+}
+
 // Single-CTA left-looking Cholesky G = L L^T (G symmetric n x n, leading dimension ldg) followed by the
 // explicit lower-triangular inverse.  LT is scratch [n][n] holding L transposed (LT[k][i] = L[i][k]) so
 // the row-parallel inner products are coalesced.  Linv is [lpad][ldi], zero outside the n x n triangle.

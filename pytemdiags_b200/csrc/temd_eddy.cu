@@ -406,9 +406,11 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     if (p.stages < 2) return temd_set_error(-1, "eddy_flux_project: not enough shared memory for lpad = %d", lpad);
     p.nch = (p.stages >= 4) ? 2 : 1;
     { const char* e = getenv("TEMD_EDDY_NCH"); if (e && atoi(e) == 1) p.nch = 1; }
-    // 16 consumer warps (4 per SM sub-partition) hide the per-chunk phase changes better than 8; the
-    // BM = 8 layout has only 8 GEMM1 units per chunk, so it stays at 8 warps.
-    int warps = (bm == 8) ? 8 : 16;
+    // Consumer warps (measured, tools/kbench.py, config 2 slab): since GEMM1 accumulates on top of the X tile (no FP64
+    // subtract in the eddy phase) 8 fat warps (2 fields x 2 n-tiles each, 0.75 LDS per DMMA) beat 16 thin ones at
+    // BM = 32: 78.5 vs 82.9 ms (before that change: 80.7 vs 78.6).  BM = 16 keeps 16 warps (only reachable with
+    // TEMD_EDDY_MODE=fused: L + 1 > 104 takes the split path); BM = 8 has only 8 GEMM1 units per chunk.
+    int warps = (bm == 16) ? 16 : 8;
     { const char* e = getenv("TEMD_EDDY_WARPS"); if (e && bm != 8) warps = atoi(e) == 8 ? 8 : 16; }
     const int nw2 = warps / (bm / 8);
     const int nj = (nt + nw2 - 1) / nw2;

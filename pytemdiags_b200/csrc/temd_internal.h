@@ -44,6 +44,8 @@ int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, cons
 // ---- K1 basis + K3 Cholesky/inverse (temd_basis.cu) ----
 int launch_basis(const double* x, int n, int L, const double* rec_a, const double* rec_b, double* qt, size_t ld,
                  int lpad, cudaStream_t stream);
+int launch_basis_dlat(const double* x, int n, int L, const double* rec_a, const double* rec_b, double* dt, size_t ld,
+                      int lpad, cudaStream_t stream);
 int launch_chol_inv(const double* G, int ldg, int n, double* LT, double* Linv, int ldi, int lpad, int* status,
                     cudaStream_t stream);
 int launch_matmul_small(const double* A, const double* B, double* C, int n, int ld, cudaStream_t stream);

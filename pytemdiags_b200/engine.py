@@ -136,6 +136,24 @@ class Engine:
         _lib.check(rc, 'temd_synth_out')
         return out.reshape(tuple(coef.shape[:-1]) + (self.Mld,))[..., :self.M]
 
+    def synth_out_dlat(self, coef):
+        """[.., rows, lpad] -> d/dphi (per radian) of the zonal means on the output latitudes, by differentiating the
+        Legendre basis (optional extra; the reference uses finite differences)."""
+        c2 = coef.reshape(-1, self.lpad)
+        out = torch.empty((c2.shape[0], self.Mld), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_synth_out_dlat(self._plan, _ptr(c2), c2.shape[0], _ptr(out), self.Mld, self.stream)
+        _lib.check(rc, 'temd_synth_out_dlat')
+        return out.reshape(tuple(coef.shape[:-1]) + (self.Mld,))[..., :self.M]
+
+    def export_dY0p(self):
+        """Dense dY0p (M, L+1): latitude derivative of the basis at the output latitudes."""
+        out = torch.empty((self.M, self.L + 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_basis_export_dlat(self._plan, _ptr(out), self.stream)
+        _lib.check(rc, 'temd_basis_export_dlat')
+        return out
+
     def synth_native(self, coef, out=None):
         c2 = coef.reshape(-1, self.lpad)
         ld = self.N + (self.N & 1)

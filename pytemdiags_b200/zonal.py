@@ -130,7 +130,7 @@ class sph_zonal_averager:
         return None if m is None else m[2]
 
     # ------------------------------------------------------------------
-    def _sph_zonal_mean_generic(self, A, native, ncol_last=False):
+    def _sph_zonal_mean_generic(self, A, native, ncol_last=False, dlat=False):
         eng = self._engine
         if not eng.built:
             raise RuntimeError('Matrices Y0, Y0inv, and/or Y0p are undefined; either verify grid_name,'
@@ -169,6 +169,8 @@ class sph_zonal_averager:
             eng.check_finite(coef, name, lambda: eng.scan_nonfinite(x2))
             if native:
                 res = eng.synth_native(coef[0])                # (DD, N)
+            elif dlat:
+                res = eng.synth_out_dlat(coef)[0]              # (DD, M)
             else:
                 res = eng.synth_out(coef)[0]                   # (DD, M)
         NN = res.shape[1]
@@ -189,7 +191,7 @@ class sph_zonal_averager:
             coords = {d: ar.coord_values(A, d) for d in dims[1:] if ar.coord_values(A, d) is not None}
             coords['lat'] = self.lat_out
             attrs = dict(DEFAULT_LAT_ATTRS)
-        attrs['long_name'] = 'zonal mean of {}'.format(name)
+        attrs['long_name'] = ('latitude derivative (per radian) of the zonal mean of {}' if dlat else 'zonal mean of {}').format(name)
         return ar.make_dataarray(A, out, odims, coords=coords, name=name, attrs=attrs)
 
     def sph_zonal_mean_native(self, A, ncol_last=False):
@@ -199,3 +201,15 @@ class sph_zonal_averager:
     def sph_zonal_mean(self, A, ncol_last=False):
         '''Zonal mean on the output latitudes (sph_zonal_mean.py:291-296).'''
         return self._sph_zonal_mean_generic(A, False, ncol_last)
+
+    def sph_zonal_mean_dlat(self, A, ncol_last=False):
+        '''Extra of this build (BASELINE.json north_star, "latitude derivatives in Legendre space"): d/dphi, per radian,
+        of `sph_zonal_mean(A)` on the output latitudes, obtained by differentiating the Legendre basis instead of
+        finite-differencing the result.  The reference has no counterpart (its lat_gradient is np.gradient,
+        tem_util.py:154) and nothing on the default TEM path uses it.'''
+        return self._sph_zonal_mean_generic(A, False, ncol_last, dlat=True)
+
+    @property
+    def dY0p(self):
+        '''(M, L+1) latitude derivative of the basis at the output latitudes.'''
+        return self._engine.export_dY0p().cpu().numpy() if self._engine.built else None

@@ -290,3 +290,32 @@ def test_to_netcdf_roundtrip(tmp_path):
     assert qpaths[0].endswith('TEM_ne4pg2_1.0deg_L10_TRACER-q0.nc')
     with netcdf_file(qpaths[0], 'r', mmap=False) as nc:
         assert np.array_equal(nc.variables['etdiv'][:], tem.etdiv())
+
+
+def test_spectral_latitude_derivative():
+    """Optional extra (north_star): Legendre-space d/dphi of the zonal mean.  dY0p against the mpmath-pinned oracle;
+    sph_zonal_mean_dlat against dY0p (Y0inv A) and, for a band-limited field, against the analytic derivative."""
+    from pytemdiags_b200 import sph_zonal_averager
+    lat, lon = syn.pg2_grid(12)
+    lat_out = np.concatenate([[-90.0], np.arange(-89.5, 90, 1.0), [90.0]])        # poles included
+    L = 30
+    for kw in ({}, {'dedup': True}):
+        ZM = sph_zonal_averager(lat, lat_out, L, **kw)
+        ZM.sph_compute_matrices()
+        dY0p = oracle.sph_basis_dlat(lat_out, L)
+        assert nerr(ZM.dY0p, dY0p) < 1e-13
+        A = np.random.default_rng(2).standard_normal((lat.shape[0], 3, 2))
+        Y0, Y0inv, Y0p = oracle.sph_matrices(lat, lat_out, L)
+        ref = (dY0p @ (Y0inv @ A.reshape(lat.shape[0], -1))).reshape((lat_out.shape[0], 3, 2))
+        got = ZM.sph_zonal_mean_dlat(A)
+        assert got.shape == ref.shape and nerr(got, ref) < TOL
+        # f = sin(phi)^2 is exactly representable (degrees 0 and 2): d/dphi = sin(2 phi)
+        f = np.sin(np.deg2rad(lat)) ** 2
+        assert np.abs(ZM.sph_zonal_mean_dlat(f) - np.sin(2 * np.deg2rad(lat_out))).max() < 1e-11
+    w = np.cos(np.deg2rad(lat)); w /= w.sum()
+    ZW = sph_zonal_averager(lat, lat_out, 8, weights=w)                           # quadrature inverse: raw derivative basis
+    ZW.sph_compute_matrices()
+    Y0 = oracle.sph_basis(lat, 8)
+    A = np.random.default_rng(3).standard_normal((lat.shape[0], 2))
+    ref = oracle.sph_basis_dlat(lat_out, 8) @ ((Y0.T * (4 * np.pi * w)) @ A)
+    assert nerr(ZW.sph_zonal_mean_dlat(A), ref) < TOL

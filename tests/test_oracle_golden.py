@@ -103,3 +103,30 @@ def test_p_integral_is_cumulative_trapezoid():
     ref = _p_integral(A, p)
     cum = np.concatenate([np.zeros((5, 1, 3)), np.cumsum(np.diff(p)[None, :, None] * (A[:, 1:] + A[:, :-1]) / 2.0, axis=1)], axis=1)
     assert np.allclose(ref, cum, rtol=1e-14, atol=1e-9)
+
+
+def test_basis_latitude_derivative_against_mpmath():
+    """Optional Legendre-space derivative (north_star): d/dphi [sqrt((2l+1)/4pi) P_l(sin phi)] from the differentiated
+    recurrence vs mpmath at 50 digits (closed form l (P_{l-1} - x P_l) / cos(phi) away from the poles, 0 at the poles),
+    and vs a centred finite difference of the SciPy basis."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    lat = np.array([-90.0, -89.5, -60.0, -12.25, 0.0, 33.0, 75.5, 89.99, 90.0])
+    L = 120
+    D = oracle.sph_basis_dlat(lat, L)
+    assert D.shape == (lat.shape[0], L + 1) and np.all(D[:, 0] == 0.0)
+    for i, la in enumerate(lat):
+        phi = mp.mpf(la) * mp.pi / 180
+        x, c = mp.sin(phi), mp.cos(phi)
+        for l in (1, 2, 3, 17, 64, 120):
+            nl = mp.sqrt((2 * l + 1) / (4 * mp.pi))
+            if abs(la) == 90.0:
+                ref = mp.mpf(0)
+            else:
+                ref = nl * l * (mp.legendre(l - 1, x) - x * mp.legendre(l, x)) / c
+            scale = float(nl) * l * (l + 1) / 2          # max |dY_l/dphi| is of this order
+            assert abs(D[i, l] - float(ref)) < 1e-12 * scale, (la, l, D[i, l], float(ref))
+    h = 1e-5
+    lat2 = np.array([-70.0, -20.0, 5.0, 48.0])
+    fd = (oracle.sph_basis(lat2 + np.rad2deg(h), 30) - oracle.sph_basis(lat2 - np.rad2deg(h), 30)) / (2 * h)
+    assert np.abs(oracle.sph_basis_dlat(lat2, 30) - fd).max() < 1e-6
