@@ -90,6 +90,13 @@ int temd_eddy_flux_project(temd_plan* plan, const double* u, const double* v, co
                            int rows, size_t ld, const double* coef4, const double* lev_scale, int nlev,
                            double* coef_flux, void* stream);
 
+/* Tracer eddy fluxes for TWO tracers at once (tem_diagnostics.py:532-538,560-570): coef4 = [4][rows][lpad] coefficient
+ * blocks of (q1, q2, v, omega); coef_flux [4][rows][lpad] = projections of q1'v', q1'omega', q2'v', q2'omega'.  The
+ * native means of v and omega are synthesised once for both tracers: 16 (L+1) flop per point per PAIR, against
+ * 14 (L+1) per tracer when temd_eddy_flux_project is called on (q, v, T, omega). */
+int temd_tracer_flux_project(temd_plan* plan, const double* q1, const double* q2, const double* v, const double* w,
+                             int rows, size_t ld, const double* coef4, double* coef_flux, void* stream);
+
 /* _compute_derivatives + the ten diagnostics methods (tem_diagnostics.py:574-797; tem_util.py:57-243).
  * zm: 7 zonal-mean arrays [nt][nlev][M] in the order ub, vb, thetab, wapb, upvpb, upwappb, vptpb.
  * gp/gl: np.gradient coefficient triplets (a,b,c) per level [3][nlev] / per latitude [3][M].

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('TEMD_LIB', os.path.join(_HERE, 'libtemd.so'))   # TEM
 SYMBOLS = (
     'temd_version', 'temd_last_error', 'temd_plan_create', 'temd_plan_destroy', 'temd_plan_lpad',
     'temd_basis_build', 'temd_basis_build_weighted', 'temd_basis_export', 'temd_project', 'temd_synth_out', 'temd_synth_native',
-    'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_host_copy', 'temd_synth_fields',
+    'temd_eddy_native', 'temd_multiply', 'temd_eddy_flux_project', 'temd_tracer_flux_project', 'temd_tem_epilogue', 'temd_tracer_epilogue', 'temd_check_finite', 'temd_host_copy', 'temd_synth_fields',
     'temd_synth_out_dlat', 'temd_basis_export_dlat', 'temd_basis_build_dedup', 'temd_group_sums', 'temd_dedup_flux', 'temd_dedup_expand',
     'temd_comm_unique_id', 'temd_comm_init', 'temd_comm_destroy', 'temd_allgather_outputs',
 )
@@ -89,6 +89,7 @@ def load():
     lib.temd_eddy_native.argtypes = [vp, vp, sz, vp, i, vp, i, vp, sz, vp]
     lib.temd_multiply.argtypes = [vp, sz, vp, sz, vp, sz, i, i, vp]
     lib.temd_eddy_flux_project.argtypes = [vp, vp, vp, vp, vp, i, sz, vp, vp, i, vp, vp]
+    lib.temd_tracer_flux_project.argtypes = [vp, vp, vp, vp, vp, i, sz, vp, vp, vp]
     lib.temd_tem_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), vp]
     lib.temd_tracer_epilogue.argtypes = [vp, C.POINTER(TracerArgs), vp]
     lib.temd_check_finite.argtypes = [vp, sz, vp]

@@ -561,36 +561,30 @@ extern "C" int temd_check_finite(const double* data, size_t n, void* stream) {
 
 namespace temd { struct EpilogueArgs { temd_epilogue_args a; }; }
 
-extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const double* v, const double* t, const double* w,
-                                      int rows, size_t ld, const double* coef4, const double* lev_scale, int nlev,
-                                      double* coef_flux, void* stream) {
-    if (p == nullptr || !p->built) return temd_set_error(-1, "eddy_flux_project: basis not built");
-    if (!u || !v || !t || !w || !coef4 || !coef_flux || rows < 1 || ld < (size_t)p->N)
-        return temd_set_error(-1, "eddy_flux_project: bad arguments");
-    if (p->weighted) return temd_set_error(-1, "eddy_flux_project: not available with the quadrature-weights inverse (TEMDiagnostics never uses it)");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TEMD_ON_DEVICE(p->dev);
+// Shared by temd_eddy_flux_project (nprod = 3: fields u, v, T, omega -> u'v', u'omega', v'theta') and
+// temd_tracer_flux_project (nprod = 4: fields q1, q2, v, omega -> q1'v', q1'omega', q2'v', q2'omega').
+static int eddy_flux_impl(temd_plan* p, const double* const* x4, int rows, size_t ld, const double* coef4,
+                          const double* lev_scale, int nlev, double* coef_flux, int nprod, cudaStream_t st) {
     const int nchunks = (p->N + 15) / 16;
-    const double* x4[4] = {u, v, t, w};
     // Two implementations of the same contraction (results agree to rounding):
     //   fused  one kernel, eddies and products never leave the SM (k_eddy): best while the 4 x 32 x lpad coefficient
     //          tile fits in shared memory (L + 1 <= 104), 32 B of HBM traffic per point;
     //   split  k_synth with the eddy epilogue writes the four eddy fields of a row batch to a scratch buffer,
-    //          k_project in product mode reads them back and projects u'v', u'omega', v'theta' (96 B per point, still far
+    //          k_project in product mode reads them back and projects the products (96 B per point, still far
     //          below the FP64 roofline for L >= 104): both are plain GEMM pipelines whose tile shapes do not shrink with L.
     const int mode = [] {          // read at every call: lets one process A/B both implementations
         const char* e = getenv("TEMD_EDDY_MODE");
         return (e && !strcmp(e, "fused")) ? 1 : (e && !strcmp(e, "split")) ? 2 : 0;
     }();
-    const bool can_fuse = eddy_supported(p->lpad);
+    const bool can_fuse = eddy_supported(p->lpad) && (nprod == 3 || p->lpad <= 104);
     const bool split = (mode == 2) || !can_fuse || (mode == 0 && p->lpad > 104);
     if (!split) {
         const int nsplit = eddy_pick_split(rows, p->lpad, nchunks, p->sms);
         double* work = nullptr;
-        int rc = ensure_work(p, st, eddy_workspace_doubles(rows, p->lpad, nsplit), &work);
+        int rc = ensure_work(p, st, eddy_workspace_doubles(rows, p->lpad, nsplit, nprod), &work);
         if (rc) return rc;
         return launch_eddy_flux_project(x4, rows, p->N, ld, p->qt, p->lpad, p->ld_q, coef4, coef_flux, work, nsplit,
-                                        lev_scale, nlev, st);
+                                        lev_scale, nlev, nprod, st);
     }
     // ---- split path, in row batches bounded by the scratch budget
     const double scratch_gb = [] { const char* e = getenv("TEMD_EDDY_SCRATCH_GB"); return (e && atof(e) > 0) ? atof(e) : 16.0; }();
@@ -607,23 +601,49 @@ extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const doubl
     project_lblocks(p->lpad, &ntb, &lblocks);
     for (size_t r0 = 0; r0 < (size_t)rows; r0 += rb) {
         const int nr = (int)std::min(rb, (size_t)rows - r0);
-        const double* xb[4] = {u + r0 * ld, v + r0 * ld, t + r0 * ld, w + r0 * ld};
-        if ((rc = launch_synth_eddy4(coef4, rows, (int)r0, nr, p->lpad, p->qt, p->N, p->ld_q, xb, ld, lev_scale, nlev, e4, ld_e, st)))
+        const double* xb[4] = {x4[0] + r0 * ld, x4[1] + r0 * ld, x4[2] + r0 * ld, x4[3] + r0 * ld};
+        if ((rc = launch_synth_eddy4(coef4, rows, (int)r0, nr, p->lpad, p->qt, p->N, p->ld_q, xb, ld, lev_scale, 2, nlev, e4, ld_e, st)))
             return rc;
-        const int tiles = ((nr + 127) / 128) * 3;
+        const int tiles = ((nr + 127) / 128) * nprod;
         const int nsplit = project_pick_split(tiles * lblocks, nchunks, p->sms, 64);
-        const size_t part_d = project_workspace_doubles(3, nr, p->lpad, nsplit), tmp_d = (size_t)3 * nr * p->lpad;
+        const size_t part_d = project_workspace_doubles(nprod, nr, p->lpad, nsplit), tmp_d = (size_t)nprod * nr * p->lpad;
         double* work = nullptr;
         if ((rc = ensure_work(p, st, part_d + tmp_d, &work))) return rc;
-        const double* pairs[6] = {e4[0], e4[1], e4[0], e4[3], e4[1], e4[2]};   // u'v', u'omega', v'theta'
+        const double* pairs3[6] = {e4[0], e4[1], e4[0], e4[3], e4[1], e4[2]};                   // u'v', u'omega', v'theta'
+        const double* pairs4[8] = {e4[0], e4[2], e4[0], e4[3], e4[1], e4[2], e4[1], e4[3]};     // q1'v', q1'w', q2'v', q2'w'
         double* tmp = (nr == rows) ? coef_flux : work + part_d;
-        if ((rc = launch_project_products(pairs, 3, nr, p->N, ld_e, p->qt, p->lpad, p->ld_q, tmp, work, nsplit, st))) return rc;
+        if ((rc = launch_project_products(nprod == 3 ? pairs3 : pairs4, nprod, nr, p->N, ld_e, p->qt, p->lpad, p->ld_q, tmp, work,
+                                          nsplit, st)))
+            return rc;
         if (nr != rows)
             TEMD_CUDA(cudaMemcpy2DAsync(coef_flux + r0 * p->lpad, (size_t)rows * p->lpad * sizeof(double), tmp,
-                                        (size_t)nr * p->lpad * sizeof(double), (size_t)nr * p->lpad * sizeof(double), 3,
+                                        (size_t)nr * p->lpad * sizeof(double), (size_t)nr * p->lpad * sizeof(double), nprod,
                                         cudaMemcpyDeviceToDevice, st));
     }
     return 0;
+}
+
+extern "C" int temd_eddy_flux_project(temd_plan* p, const double* u, const double* v, const double* t, const double* w,
+                                      int rows, size_t ld, const double* coef4, const double* lev_scale, int nlev,
+                                      double* coef_flux, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "eddy_flux_project: basis not built");
+    if (!u || !v || !t || !w || !coef4 || !coef_flux || rows < 1 || ld < (size_t)p->N)
+        return temd_set_error(-1, "eddy_flux_project: bad arguments");
+    if (p->weighted) return temd_set_error(-1, "eddy_flux_project: not available with the quadrature-weights inverse (TEMDiagnostics never uses it)");
+    TEMD_ON_DEVICE(p->dev);
+    const double* x4[4] = {u, v, t, w};
+    return eddy_flux_impl(p, x4, rows, ld, coef4, lev_scale, nlev, coef_flux, 3, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int temd_tracer_flux_project(temd_plan* p, const double* q1, const double* q2, const double* v, const double* w,
+                                        int rows, size_t ld, const double* coef4, double* coef_flux, void* stream) {
+    if (p == nullptr || !p->built) return temd_set_error(-1, "tracer_flux_project: basis not built");
+    if (!q1 || !q2 || !v || !w || !coef4 || !coef_flux || rows < 1 || ld < (size_t)p->N)
+        return temd_set_error(-1, "tracer_flux_project: bad arguments");
+    if (p->weighted) return temd_set_error(-1, "tracer_flux_project: not available with the quadrature-weights inverse");
+    TEMD_ON_DEVICE(p->dev);
+    const double* x4[4] = {q1, q2, v, w};
+    return eddy_flux_impl(p, x4, rows, ld, coef4, nullptr, 1, coef_flux, 4, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int temd_tem_epilogue(temd_plan* p, const temd_epilogue_args* args, void* stream) {

@@ -63,32 +63,37 @@ __host__ __device__ inline int eddy_ls(int lpad) {
     return ls;
 }
 
-// GEMM2 inner step for one 16-column chunk: CNT (<= NJ) n8-tiles of this warp, 3 flux products.
-// PAIRED: the eddy phase already left v'theta' in the theta tile and u'omega' in the omega tile (see below), so
-// only u'v' is formed here.
-template <int CNT, int NJ, int XF_BYTES, bool PAIRED>
-__device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st, uint32_t qs, uint32_t e_row_off,
+// GEMM2 inner step for one 16-column chunk: CNT (<= NJ) n8-tiles of this warp.
+//   NP = 3 (TEM): products u'v', u'omega', v'theta' of the fields (u, v, theta, omega).  PAIRED: the eddy phase already
+//       left v'theta' in the theta tile and u'omega' in the omega tile (see below), so only u'v' is formed here.
+//   NP = 4 (tracer pair): fields (q1, q2, v, omega), products q1'v', q1'omega', q2'v', q2'omega'
+//       (tem_diagnostics.py:560-570 for two tracers at once: v' and omega' are synthesised once for both).
+template <int CNT, int NJ, int XF_BYTES, bool PAIRED, int NP>
+__device__ __forceinline__ void eddy_gemm2(double (&acc)[NP][NJ][2], uint32_t st, uint32_t qs, uint32_t e_row_off,
                                            const uint32_t (&coff2)[4], int g, int j_begin) {
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
         const uint32_t eo = st + e_row_off + coff2[kk];
-        const double eu = lds64(eo);
-        const double ev = lds64(eo + XF_BYTES);
-        const double et = lds64(eo + 2 * XF_BYTES);
-        const double ew = lds64(eo + 3 * XF_BYTES);
-        const double a_uv = eu * ev;
-        const double a_uw = PAIRED ? ew : eu * ew;
-        const double a_vt = PAIRED ? et : ev * et;
+        const double e0 = lds64(eo);
+        const double e1 = lds64(eo + XF_BYTES);
+        const double e2 = lds64(eo + 2 * XF_BYTES);
+        const double e3 = lds64(eo + 3 * XF_BYTES);
+        double a[NP];
+        if constexpr (NP == 3) {
+            a[0] = e0 * e1;
+            a[1] = PAIRED ? e3 : e0 * e3;
+            a[2] = PAIRED ? e2 : e1 * e2;
+        } else {
+            a[0] = e0 * e2; a[1] = e0 * e3; a[2] = e1 * e2; a[3] = e1 * e3;
+        }
         const uint32_t bo = qs + (uint32_t)((j_begin * 8 + g) * TILE_ROW_BYTES) + coff2[kk];
         double b[CNT];
 #pragma unroll
         for (int jj = 0; jj < CNT; jj++) b[jj] = lds64(bo + (uint32_t)jj * 8u * TILE_ROW_BYTES);
 #pragma unroll
-        for (int jj = 0; jj < CNT; jj++) {
-            dmma(acc[0][jj][0], acc[0][jj][1], a_uv, b[jj]);
-            dmma(acc[1][jj][0], acc[1][jj][1], a_uw, b[jj]);
-            dmma(acc[2][jj][0], acc[2][jj][1], a_vt, b[jj]);
-        }
+        for (int jj = 0; jj < CNT; jj++)
+#pragma unroll
+            for (int q = 0; q < NP; q++) dmma(acc[q][jj][0], acc[q][jj][1], a[q], b[jj]);
     }
 }
 
@@ -99,7 +104,7 @@ __device__ __forceinline__ void eddy_gemm2(double (&acc)[3][NJ][2], uint32_t st,
 // the pool cannot satisfy makes setmaxnreg.inc spin forever.)
 template <int WARPS> constexpr int eddy_producer_warps() { return WARPS == 16 ? 4 : 1; }
 
-template <int BM, int NJ, int WARPS, bool TWO>
+template <int BM, int NJ, int WARPS, bool TWO, int NP>
 __global__ void __launch_bounds__((WARPS + eddy_producer_warps<WARPS>()) * 32, 1)
 k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     constexpr int MT = BM / 8;          // m8-tiles per CTA
@@ -191,7 +196,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     // fields: 0 = u, 1 = v, 2 = theta, 3 = omega.  With two fields per warp the pairs are {u, omega} and {v, theta}:
     // each warp can then form one flux product (u'omega' resp. v'theta') from its own registers in the eddy phase
     // and store it over the second field's tile, which nobody needs any more; GEMM2 multiplies only u'v'.
-    constexpr bool PAIRED = (NF1 == 2);
+    constexpr bool PAIRED = (NF1 == 2) && (NP == 3);   // the tracer-pair mode needs every eddy twice: nothing to overwrite
     int fid[NF1];
     if (PAIRED) {
         const int pr = (NW2 == 2) ? r_in : (r_in & 1);
@@ -214,9 +219,9 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
         if (p.lev_scale != nullptr && row < p.rows) tscale = p.lev_scale[row % p.nlev];
     }
 
-    double acc[3][NJ][2];
+    double acc[NP][NJ][2];
 #pragma unroll
-    for (int a = 0; a < 3; a++)
+    for (int a = 0; a < NP; a++)
 #pragma unroll
         for (int j = 0; j < NJ; j++) acc[a][j][0] = acc[a][j][1] = 0.0;
 
@@ -300,14 +305,15 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
                 }
                 sts128(st[c] + fid[0] * XF_BYTES + off, e0[0], e1[0]);
                 if (PAIRED) sts128(st[c] + fid[NF1 - 1] * XF_BYTES + off, e0[0] * e0[NF1 - 1], e1[0] * e1[NF1 - 1]);
+                else if (NF1 == 2) sts128(st[c] + fid[NF1 - 1] * XF_BYTES + off, e0[NF1 - 1], e1[NF1 - 1]);
             }
         named_bar_sync(grp_bar, grp_threads);
 
         // ---------------- GEMM2: acc += (E_a .* E_b) * QT^T (contraction over the 16 columns) ----------------
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-            if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES, PAIRED>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
-            else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES, PAIRED>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
+            if (j_cnt == NJ) eddy_gemm2<NJ, NJ, XF_BYTES, PAIRED, NP>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
+            else eddy_gemm2<(NJ > 1 ? NJ - 1 : 1), NJ, XF_BYTES, PAIRED, NP>(acc, st[c], qs[c], e_row_off, coff2, g, j_begin);
         }
         // the E tiles were written through the generic proxy; order them before the next TMA refill
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -330,8 +336,8 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     const int row = row0 + mi * 8 + g;
     if (row < p.rows) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            double* out = p.part + (((size_t)split * 3 + a) * p.rows + row) * lpad;
+        for (int a = 0; a < NP; a++) {
+            double* out = p.part + (((size_t)split * NP + a) * p.rows + row) * lpad;
 #pragma unroll
             for (int jj = 0; jj < NJ; jj++) {
                 if (jj < j_cnt) *reinterpret_cast<double2*>(out + (j_begin + jj) * 8 + 2 * t) = make_double2(acc[a][jj][0], acc[a][jj][1]);
@@ -359,26 +365,34 @@ int eddy_pick_split(int rows, int lpad, int nchunks, int sms) {
     return project_pick_split((rows + bm - 1) / bm, nchunks, sms, 64);
 }
 
-size_t eddy_workspace_doubles(int rows, int lpad, int nsplit) { return (size_t)nsplit * 3 * rows * lpad; }
+size_t eddy_workspace_doubles(int rows, int lpad, int nsplit, int nprod) { return (size_t)nsplit * nprod * rows * lpad; }
 
-template <int BM, int NJ, int WARPS, bool TWO>
+template <int BM, int NJ, int WARPS, bool TWO, int NP>
 static int launch_eddy_2(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ, WARPS, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_eddy<BM, NJ, WARPS, TWO, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int ntiles = (p.rows + BM - 1) / BM;
-    k_eddy<BM, NJ, WARPS, TWO><<<ntiles * p.nsplit, (WARPS + eddy_producer_warps<WARPS>()) * 32, smem, stream>>>(maps, p);
+    k_eddy<BM, NJ, WARPS, TWO, NP><<<ntiles * p.nsplit, (WARPS + eddy_producer_warps<WARPS>()) * 32, smem, stream>>>(maps, p);
     return (int)cudaGetLastError();
 }
 
 template <int BM, int NJ, int WARPS>
 static int launch_eddy_t(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
-    return p.nch == 2 ? launch_eddy_2<BM, NJ, WARPS, true>(maps, p, smem, stream)
-                      : launch_eddy_2<BM, NJ, WARPS, false>(maps, p, smem, stream);
+    return p.nch == 2 ? launch_eddy_2<BM, NJ, WARPS, true, 3>(maps, p, smem, stream)
+                      : launch_eddy_2<BM, NJ, WARPS, false, 3>(maps, p, smem, stream);
+}
+
+// tracer-pair instantiation (4 products): BM = 32, 8 consumer warps, one chunk per round (the fourth accumulator set
+// takes the registers the second chunk's GEMM1 accumulators would need)
+template <int NJ>
+static int launch_eddy_pair(const EddyMaps& maps, const EddyParams& p, int smem, cudaStream_t stream) {
+    return launch_eddy_2<32, NJ, 8, false, 4>(maps, p, smem, stream);
 }
 
 int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t ld_x, const double* qt, int lpad,
                              size_t ld_q, const double* coef4, double* coef_flux, double* part, int nsplit,
-                             const double* lev_scale, int nlev, cudaStream_t stream) {
+                             const double* lev_scale, int nlev, int nprod, cudaStream_t stream) {
+    if (nprod != 3 && nprod != 4) return temd_set_error(-1, "eddy_flux_project: nprod must be 3 (TEM) or 4 (tracer pair)");
     if (!eddy_supported(lpad)) return temd_set_error(-1, "eddy_flux_project: L+1 > 408 is not supported by the fused kernel");
     const int nt = lpad / 8;
     const int bm = eddy_bm(nt);
@@ -412,9 +426,22 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     // TEMD_EDDY_MODE=fused: L + 1 > 104 takes the split path); BM = 8 has only 8 GEMM1 units per chunk.
     int warps = (bm == 16) ? 16 : 8;
     { const char* e = getenv("TEMD_EDDY_WARPS"); if (e && bm != 8) warps = atoi(e) == 8 ? 8 : 16; }
+    rc = -1;
+    if (nprod == 4) {
+        if (bm != 32) return temd_set_error(-1, "eddy_flux_project: the tracer-pair kernel serves L + 1 <= 104 (larger L uses the split path)");
+        p.nch = 1;
+        const int nj = (nt + 1) / 2;
+        switch (nj) {
+#define PCASE(N) case N: rc = launch_eddy_pair<N>(maps, p, smem, stream); break;
+            PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7)
+#undef PCASE
+            default: break;
+        }
+        if (rc) return temd_set_error(rc, "eddy_flux_project: tracer-pair kernel launch failed (nj %d)", nj);
+        return launch_reduce_partials(part, coef_flux, nsplit, 4, rows, lpad, nullptr, -1, 1, stream);
+    }
     const int nw2 = warps / (bm / 8);
     const int nj = (nt + nw2 - 1) / nw2;
-    rc = -1;
 #define ED_CASE(BM_, NJ_, W_) if (bm == BM_ && nj == NJ_ && warps == W_) rc = launch_eddy_t<BM_, NJ_, W_>(maps, p, smem, stream);
 #define ED_CASES7(BM_, W_) ED_CASE(BM_, 1, W_) ED_CASE(BM_, 2, W_) ED_CASE(BM_, 3, W_) ED_CASE(BM_, 4, W_) ED_CASE(BM_, 5, W_) ED_CASE(BM_, 6, W_) ED_CASE(BM_, 7, W_)
 #define ED_CASES4(BM_, W_) ED_CASE(BM_, 1, W_) ED_CASE(BM_, 2, W_) ED_CASE(BM_, 3, W_) ED_CASE(BM_, 4, W_)

@@ -35,8 +35,8 @@ int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double*
                  size_t ld_out, cudaStream_t stream);
 
 int launch_synth_eddy4(const double* coef4, int rows_total, int r0, int rows, int lpad, const double* b, int ncol, size_t ld_b,
-                       const double* const* x, size_t ld_x, const double* lev_scale, int nlev, double* const* out,
-                       size_t ld_out, cudaStream_t stream);
+                       const double* const* x, size_t ld_x, const double* lev_scale, int scale_field, int nlev,
+                       double* const* out, size_t ld_out, cudaStream_t stream);
 
 int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, const double* b, int ncol, size_t ld_b,
                           double* out, size_t ld_out, int sms, cudaStream_t stream);
@@ -53,10 +53,10 @@ int launch_matmul_small(const double* A, const double* B, double* C, int n, int 
 // ---- K5 fused eddy / flux / projection (temd_eddy.cu) ----
 int eddy_supported(int lpad);
 int eddy_pick_split(int rows, int lpad, int nchunks, int sms);
-size_t eddy_workspace_doubles(int rows, int lpad, int nsplit);
+size_t eddy_workspace_doubles(int rows, int lpad, int nsplit, int nprod);
 int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t ld_x, const double* qt, int lpad,
                              size_t ld_q, const double* coef4, double* coef_flux, double* part, int nsplit,
-                             const double* lev_scale, int nlev, cudaStream_t stream);
+                             const double* lev_scale, int nlev, int nprod, cudaStream_t stream);
 
 // ---- K6 stencil epilogue (temd_epilogue.cu) ----
 struct EpilogueArgs;

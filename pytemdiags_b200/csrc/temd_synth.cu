@@ -186,13 +186,13 @@ int launch_synth(const double* c, int rows, int lpad, size_t ld_c, const double*
 // Eddy fields of a row batch: out[f][r][n] = lev_scale * x[f][r0 + r][n] - (C_f B)[r0 + r][n], r < rows, f < 4
 // (coef4 is [4][rows_total][lpad]; x[f] / out[f] point at the batch's first row).
 int launch_synth_eddy4(const double* coef4, int rows_total, int r0, int rows, int lpad, const double* b, int ncol, size_t ld_b,
-                       const double* const* x, size_t ld_x, const double* lev_scale, int nlev, double* const* out,
-                       size_t ld_out, cudaStream_t stream) {
+                       const double* const* x, size_t ld_x, const double* lev_scale, int scale_field, int nlev,
+                       double* const* out, size_t ld_out, cudaStream_t stream) {
     SynthEpi epi = {};
     for (int f = 0; f < 4; f++) { epi.x[f] = x[f]; epi.out[f] = out[f]; }
     epi.ld_x = ld_x;
     epi.lev_scale = lev_scale;
-    epi.scale_field = 2;
+    epi.scale_field = lev_scale ? scale_field : -1;
     epi.nlev = nlev < 1 ? 1 : nlev;
     epi.c_field_rows = rows_total;
     epi.row_base = r0;

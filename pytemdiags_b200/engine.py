@@ -244,10 +244,29 @@ class Engine:
         rows = xs[0].shape[0]
         out = torch.empty((3 * len(qs), rows, self.lpad), dtype=torch.float64, device=self.device)
         cq_all = torch.cat([self.project(list(qs[i:i + 8])) for i in range(0, len(qs), 8)], 0)
-        for i, q in enumerate(qs):
-            out[3 * i] = cq_all[i]
+        out[0::3] = cq_all
+        i = 0
+        while i + 1 < len(qs):       # two tracers per launch: v' and omega' are synthesised once for the pair
+            c4p = torch.cat([cq_all[i:i + 2], c4[1:2], c4[3:4]], 0)
+            fl = self.tracer_flux_project(qs[i], qs[i + 1], xs[1], xs[3], c4p)
+            out[3 * i + 1:3 * i + 3] = fl[0:2]
+            out[3 * i + 4:3 * i + 6] = fl[2:4]
+            i += 2
+        if i < len(qs):              # an odd tracer out: the TEM kernel on (q, v, theta, omega), first two product slots
             c4q = torch.cat([cq_all[i:i + 1], c4[1:]], 0)
-            out[3 * i + 1:3 * i + 3] = self.eddy_flux_project(q, xs[1], xs[2], xs[3], c4q, lev_scale, nlev)[:2]
+            out[3 * i + 1:3 * i + 3] = self.eddy_flux_project(qs[i], xs[1], xs[2], xs[3], c4q, lev_scale, nlev)[:2]
+        return out
+
+    def tracer_flux_project(self, q1, q2, v, w, coef4):
+        """coef4 = [4][rows][lpad] coefficients of (q1, q2, v, omega) -> [4][rows][lpad] of q1'v', q1'omega', q2'v', q2'omega'."""
+        for x in (q1, q2, v, w):
+            self._check_field(x)
+        rows, ld = v.shape[0], v.stride(0)
+        out = torch.empty((4, rows, self.lpad), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.temd_tracer_flux_project(self._plan, _ptr(q1), _ptr(q2), _ptr(v), _ptr(w), rows, ld,
+                                                   _ptr(coef4.contiguous()), _ptr(out), self.stream)
+        _lib.check(rc, 'temd_tracer_flux_project')
         return out
 
     def tem_epilogue(self, zm, p_pa, f, coslat, p0=P0):

@@ -319,3 +319,29 @@ def test_spectral_latitude_derivative():
     A = np.random.default_rng(3).standard_normal((lat.shape[0], 2))
     ref = oracle.sph_basis_dlat(lat_out, 8) @ ((Y0.T * (4 * np.pi * w)) @ A)
     assert nerr(ZW.sph_zonal_mean_dlat(A), ref) < TOL
+
+
+@pytest.mark.parametrize('L', [24, 120])        # fused tracer-pair kernel / split path in pair mode
+def test_several_tracers_pair_kernel(L):
+    """Tracers are processed two per launch (temd_tracer_flux_project: q1'v', q1'omega', q2'v', q2'omega' with v' and
+    omega' synthesised once) plus the TEM kernel for an odd one out.  Every tracer must give what it gives alone
+    (the single-tracer path is pinned against the unmodified reference by the golden fixture)."""
+    from pytemdiags_b200 import TEMDiagnostics
+    lat, lon = syn.pg2_grid(10)
+    K, T = 6, 3
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=31, fields=('ua', 'va', 'ta', 'wap', 'q'))
+    rng = np.random.default_rng(8)
+    qs = [f['q'], f['q'] * 0.5 + 1e-4 * rng.standard_normal(f['q'].shape), 3e-4 * np.abs(f['va']) + 1e-5]
+    kw = dict(L=L, dims=('time', 'lev', 'ncol'), debug_level=0)
+    both = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, q=qs, **kw)
+    assert both.ntrac == 3
+    for i, q in enumerate(qs):
+        alone = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, q=q, **kw)
+        for m in ('etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem'):
+            e = nerr(getattr(both, m)(i), getattr(alone, m)(0))
+            assert e < 1e-11, (i, m, e)
+        for p_ in ('qb', 'qpvpb', 'qpwappb', 'dqb_dp'):
+            assert nerr(getattr(both, p_)[i], getattr(alone, p_)[0]) < 1e-11, (i, p_)
+    with pytest.raises(RuntimeError, match='qi must be passed'):
+        both.etfy()
