@@ -198,7 +198,7 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     // and store it over the second field's tile, which nobody needs any more; GEMM2 multiplies only u'v'.
     constexpr bool PAIRED = (NF1 == 2) && (NP == 3);   // the tracer-pair mode needs every eddy twice: nothing to overwrite
     int fid[NF1];
-    if (PAIRED) {
+    if (NF1 == 2) {                  // field pairs {0, 3} and {1, 2}: {u, omega} / {v, theta}, or {q1, omega} / {q2, v}
         const int pr = (NW2 == 2) ? r_in : (r_in & 1);
         fid[0] = pr;                 // u or v
         fid[NF1 - 1] = 3 - pr;       // omega or theta
