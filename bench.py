@@ -562,6 +562,13 @@ def run_record(ctx, cfgname, sub_steps, dedup=False):
                            'achieved': gb / (g_ms * 1e-3) / 1e9, 'peak': hb, 'unit': 'GB/s',
                            'algorithmic_bytes': '32 B per col.lev.step (four float64 fields read once)'}
         out['roofline']['frac'] = out['roofline']['achieved'] / hb
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('%s:%d:dedup' % (cfgname, sub_steps))
+            if tr:      # ncu dram bytes of ONE launch over one sub-slab, next to its algorithmic bytes
+                out['roofline']['traffic'] = tr['k_gsum_warp']['dram_bytes']
+                out['roofline']['algorithmic_bytes_per_launch'] = tr['k_gsum_warp']['algorithmic_bytes']
+        except Exception:
+            pass
         out['suite_hbm'] = {'achieved_gbs': gb / (total_ms * 1e-3) / 1e9, 'frac': gb / (total_ms * 1e-3) / 1e9 / hb,
                             'note': 'whole suite incl. the tensor-core kernels on the unique grid and the tail'}
     else:

@@ -222,7 +222,7 @@ extern "C" int temd_plan_create(int device, int ncol, int L, int nlat_out, temd_
     *out = nullptr;
     if (ncol < 1 || L < 0 || nlat_out < 1) return temd_set_error(-1, "plan_create: bad sizes (ncol %d, L %d, M %d)", ncol, L, nlat_out);
     if (L + 1 > 1024) return temd_set_error(-1, "plan_create: L = %d exceeds the supported maximum 1023", L);
-    if (L + 1 > ncol) return temd_set_error(-1, "plan_create: L+1 = %d exceeds ncol = %d (Y0 would be rank-deficient)", L + 1, ncol);
+    if (L + 1 > ncol) return temd_set_error(-1, "plan_create: L+1 = %d exceeds ncol = %d (Y0 would be rank-deficient: lower L; the reference's lstsq would return a minimum-norm solution here, this build does not)", L + 1, ncol);
     TEMD_ON_DEVICE(device);
     cudaDeviceProp prop;
     TEMD_CUDA(cudaGetDeviceProperties(&prop, device));
