@@ -15,6 +15,7 @@ Extra blocks in the same JSON line (`records`), each a whole BASELINE record tim
 (STRONG scaling; slabs generated on the device, kernels timed with CUDA events, max over ranks, final gather included):
   config3  ne256pg2 x 128 lev x 96 steps, L=200 (the north-star record)
   config4  0.25-degree lat-lon x 37 lev x 240 steps, L=300: dense path and the de-duplicated fast path (`dedup=True`)
+  config2_dedup  the 365-step ne120pg2 record through the de-duplicated path (scattered groups of <= 8 columns)
   config5  zonal-mean-only sweep L in {25..800} on ne120pg2 x 72 lev x 24 steps (N = 1 only)
 Each carries its roofline fractions and a spot check of one time step against tests/golden/scale_*.npz.
 
@@ -402,61 +403,90 @@ def h2d_ceiling(ctx, nbytes):
 
 def e2e_leg(args, ctx, head, xs, plev, lat):
     """The public API on pinned HOST arrays, H2D + D2H inside the timed region.  N = 1: TEMDiagnostics; N > 1:
-    ShardedTEM (each rank uploads its slab) + gather_all() (one collective) + D2H of the gathered outputs."""
+    ShardedTEM (each rank uploads its slab) + gather_all() (one collective) + D2H of the gathered outputs.  At N > 1
+    the record of e2e_steps x N time steps is sharded twice: equally, and in proportion to the host->device bandwidth
+    each GPU gets when all ranks copy at once (`ShardedTEM(weights=...)`): on this pool's 8-GPU boxes GPUs 0-3 get
+    23 GB/s and GPUs 4-7 35 GB/s, so an equal split waits for the slow links."""
     torch = ctx.torch
     from pytemdiags_b200 import TEMDiagnostics
-    from pytemdiags_b200.distributed import ShardedTEM
+    from pytemdiags_b200.distributed import ShardedTEM, shard_bounds
     N, K, L, Te = head['N'], head['K'], head['L'], args.e2e_steps
-    host = []
-    for fi in range(4):
-        h = torch.empty((Te, K, N), dtype=torch.float64).pin_memory()
-        h.copy_(xs[fi][:Te * K].reshape(Te, K, N))
-        host.append(h.numpy())
-    torch.cuda.synchronize()
-    h2d = 4 * Te * K * N * 8
     M = 180
     kw = dict(L=L, dims=('time', 'lev', 'ncol'), debug_level=0, device=ctx.dev)
+    ceiling = h2d_ceiling(ctx, min(4 * Te * K * N * 8 // 4, 2 << 30))
+    Ttot = Te * ctx.world
 
-    if ctx.world == 1:
-        d2h = 10 * M * K * Te * 8
-
-        def call():
-            tem = TEMDiagnostics(host[0], host[1], host[2], host[3], plev, lat, **kw)
-            return [getattr(tem, n)() for n in PUBLIC]
-    else:
-        d2h = 10 * M * K * Te * ctx.world * 8
-
-        def call():
-            sh = ShardedTEM(host[0], host[1], host[2], host[3], plev, lat, T=Te * ctx.world, **kw)
-            full = sh.gather_all(tracers=False, layout='device')
-            return [full[n].cpu() for n in PUBLIC]
-    ceiling = h2d_ceiling(ctx, min(h2d // 4, 2 << 30))
-    for _ in range(2):
-        call()
-    ctx.barrier()
-    nrep = 5
-    a, b = ev_pair(torch)
-    calls = []
-    a.record()
-    for _ in range(nrep):
-        tc = time.time()
-        call()
+    def measure(weights):
+        a_, b_ = shard_bounds(Ttot, ctx.world, weights)[ctx.rank]
+        nloc = b_ - a_
+        assert nloc * K <= xs[0].shape[0], 'e2e slab larger than the resident slab'
+        host = []
+        for fi in range(4):
+            h = torch.empty((nloc, K, N), dtype=torch.float64).pin_memory()
+            h.copy_(xs[fi][:nloc * K].reshape(nloc, K, N))
+            host.append(h.numpy())
         torch.cuda.synchronize()
-        calls.append(time.time() - tc)
-    b.record()
-    ctx.barrier()
-    dt = ctx.max(a.elapsed_time(b) * 1e-3 / nrep)
-    if os.environ.get('TEMD_BENCH_DEBUG'):
-        print('e2e per-call ms:', [round(c * 1e3, 1) for c in calls], file=sys.stderr)
-    val = N * K * Te * ctx.world / dt
+        if ctx.world == 1:
+            def call():
+                tem = TEMDiagnostics(host[0], host[1], host[2], host[3], plev, lat, **kw)
+                return [getattr(tem, n)() for n in PUBLIC]
+        else:
+            def call():
+                sh = ShardedTEM(host[0], host[1], host[2], host[3], plev, lat, T=Ttot, weights=weights, **kw)
+                full = sh.gather_all(tracers=False, layout='device')
+                return [full[n].cpu() for n in PUBLIC]
+        for _ in range(2):
+            call()
+        ctx.barrier()
+        nrep = 5
+        a, b = ev_pair(torch)
+        calls = []
+        a.record()
+        for _ in range(nrep):
+            tc = time.time()
+            call()
+            torch.cuda.synchronize()
+            calls.append(time.time() - tc)
+        b.record()
+        ctx.barrier()
+        dt = ctx.max(a.elapsed_time(b) * 1e-3 / nrep)
+        if os.environ.get('TEMD_BENCH_DEBUG'):
+            print('e2e per-call ms:', [round(c * 1e3, 1) for c in calls], file=sys.stderr)
+        del host
+        return dt, [y - x for x, y in shard_bounds(Ttot, ctx.world, weights)]
+
+    dt, steps = measure(None)
+    h2d = 4 * Ttot * K * N * 8                     # bytes all ranks upload per call
+    d2h = 10 * M * K * Ttot * 8 * ctx.world        # every rank reads the gathered outputs back
     bound = ceiling['concurrent_aggregate_gbs'] * 1e9 / 32.0
-    return {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'time_steps_per_call': Te,
-            'ms_per_call': dt * 1e3, 'h2d_gbs_achieved_per_gpu': h2d / dt / 1e9, 'h2d_ceiling': ceiling,
-            'ceiling_value': bound, 'frac_of_h2d_ceiling': val / bound, 'cpu_binding': ctx.binding,
-            'api': 'TEMDiagnostics(ua, va, ta, wap, p, lat)' if ctx.world == 1 else
-                   'ShardedTEM(ua, va, ta, wap, p, lat, T=...).gather_all()  (one NCCL all-gather of the 10 outputs)',
-            'note': 'pinned host arrays; H2D of slab i+1 overlaps compute of slab i; basis cached across calls like the '
-                    'reference\'s maps/ cache; the metric is bound by host->device bandwidth (32 B per point)'}
+    out = {'value': N * K * Ttot / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'time_steps_per_call': Ttot, 'time_steps_per_gpu': steps, 'ms_per_call': dt * 1e3,
+           'h2d_gbs_achieved_aggregate': h2d / dt / 1e9, 'h2d_ceiling': ceiling,
+           'ceiling_value': bound, 'frac_of_h2d_ceiling': N * K * Ttot / dt / bound, 'cpu_binding': ctx.binding,
+           'api': 'TEMDiagnostics(ua, va, ta, wap, p, lat)' if ctx.world == 1 else
+                  'ShardedTEM(ua, va, ta, wap, p, lat, T=..., weights=...).gather_all()  (one NCCL all-gather of the 10 outputs)',
+           'note': 'pinned host arrays; H2D of slab i+1 overlaps compute of slab i; basis cached across calls like the '
+                   'reference\'s maps/ cache; the metric is bound by host->device bandwidth (32 B per point): ceiling_value = '
+                   'concurrent aggregate H2D GB/s / 32 B'}
+    if ctx.world > 1:
+        equal = {'value': out['value'], 'ms_per_call': out['ms_per_call'], 'time_steps_per_gpu': steps,
+                 'frac_of_h2d_ceiling': out['frac_of_h2d_ceiling'],
+                 'frac_of_slowest_link_ceiling': N * K * Ttot / dt / (ctx.world * min(ceiling['concurrent_gbs_per_gpu']) * 1e9 / 32.0)}
+        w = ceiling['concurrent_gbs_per_gpu']
+        out['sharding'] = 'equal'
+        if max(w) / min(w) > 1.1:       # heterogeneous host links: slabs proportional to the measured bandwidth
+            dtw, stepsw = measure(w)
+            weighted = {'value': N * K * Ttot / dtw, 'ms_per_call': dtw * 1e3, 'time_steps_per_gpu': stepsw,
+                        'frac_of_h2d_ceiling': N * K * Ttot / dtw / bound, 'weights_gbs': w}
+            out['equal_split'] = equal
+            out['weighted_split'] = weighted
+            if weighted['value'] > out['value']:
+                out.update(value=weighted['value'], ms_per_call=weighted['ms_per_call'], time_steps_per_gpu=stepsw,
+                           frac_of_h2d_ceiling=weighted['frac_of_h2d_ceiling'],
+                           h2d_gbs_achieved_aggregate=h2d / dtw / 1e9, sharding='weighted by measured concurrent H2D GB/s')
+        else:
+            out['equal_split'] = equal
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -655,7 +685,8 @@ def run_ours(args):
     if not args.no_records:
         todo = [('config3', lambda: run_record(ctx, 'config3', 12)),
                 ('config4', lambda: run_record(ctx, 'config4', 30)),
-                ('config4_dedup', lambda: run_record(ctx, 'config4', 30, dedup=True))]
+                ('config4_dedup', lambda: run_record(ctx, 'config4', 30, dedup=True)),
+                ('config2_dedup', lambda: run_record(ctx, 'config2', 73, dedup=True))]
         for name, fn in todo:
             try:
                 records[name] = fn()

@@ -20,25 +20,61 @@ PUBLIC_OUTPUTS = ('vtem', 'omegatem', 'wtem', 'psitem', 'epfy', 'epfz', 'epdiv',
 TRACER_PUBLIC = ('etfy', 'etfz', 'etdiv', 'qtendetfd', 'qtendvtem', 'qtendwtem')
 
 
-def shard_bounds(T, world):
-    """Contiguous, balanced time slabs: returns [(t0, t1)] * world; the first T % world ranks get one extra step."""
-    base, extra = divmod(int(T), int(world))
-    out, t = [], 0
-    for r in range(world):
-        n = base + (1 if r < extra else 0)
-        out.append((t, t + n))
-        t += n
-    return out
+def shard_bounds(T, world, weights=None):
+    """Contiguous time slabs: returns [(t0, t1)] * world.  Without weights the slabs are balanced (the first T % world
+    ranks get one extra step).  `weights` (one positive number per rank, identical on every rank) makes rank r's slab
+    proportional to weights[r] - e.g. the host->device bandwidth each GPU really gets (`h2d_weights`): on boxes whose
+    GPUs do not share the host links evenly an equal split makes everybody wait for the slowest link."""
+    T, world = int(T), int(world)
+    if weights is None:
+        base, extra = divmod(T, world)
+        out, t = [], 0
+        for r in range(world):
+            n = base + (1 if r < extra else 0)
+            out.append((t, t + n))
+            t += n
+        return out
+    w = np.asarray(weights, dtype=np.float64)
+    if w.shape != (world,) or not np.all(w > 0):
+        raise ValueError('weights must be %d positive numbers' % world)
+    edges = np.rint(T * np.concatenate([[0.0], np.cumsum(w)]) / w.sum()).astype(np.int64)
+    edges[-1] = T
+    return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
 
 
-def gather_time_major(local, T, group=None, comm=None):
+def h2d_weights(device, group=None, nbytes=256 << 20, reps=3):
+    """Host->device bandwidth (GB/s) every rank gets while ALL ranks copy at once, as a list identical on every rank:
+    the `weights` for `shard_bounds` / `ShardedTEM` when the inputs live in host memory.  (8xB200 box of this pool:
+    55.6 GB/s per GPU alone, 23.3 / 35.4 GB/s for GPUs 0-3 / 4-7 when all eight copy.)"""
+    device = torch.device(device)
+    n = int(nbytes) // 8
+    h = torch.empty(n, dtype=torch.float64).pin_memory()
+    h.zero_()
+    d = torch.empty(n, dtype=torch.float64, device=device)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(device)
+    dist.barrier(group)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.device(device):
+        a.record()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(device)
+    rate = torch.tensor([reps * n * 8 / (a.elapsed_time(b) * 1e-3) / 1e9], dtype=torch.float64, device=device)
+    out = torch.empty(dist.get_world_size(group), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, rate, group=group)
+    return [float(x) for x in out.cpu()]
+
+
+def gather_time_major(local, T, group=None, comm=None, weights=None):
     """ONE all-gather of per-rank blocks shaped (P, T_local, ...) (time second: the device layout
     [plane][time][lev][lat]) into the full (P, T, ...) array on every rank.  Uneven slabs (and empty ones,
     T_local = 0) are zero-padded to the largest slab for the equal-count collective and trimmed afterwards.
     `comm`: a `TemdComm` to run the collective inside libtemd instead of torch.distributed."""
     world = comm.nranks if comm is not None else dist.get_world_size(group)
     rank = comm.rank if comm is not None else dist.get_rank(group)
-    bounds = shard_bounds(T, world)
+    bounds = shard_bounds(T, world, weights)
     tmax = max(b - a for a, b in bounds)
     a, b = bounds[rank]
     assert local.shape[1] == b - a, (tuple(local.shape), bounds[rank])
@@ -119,12 +155,13 @@ class ShardedTEM:
         vtem = tem.gather('vtem')         # a single output
 
     `comm=TemdComm(...)` routes the collective through libtemd's own NCCL call instead of torch.distributed.
+    `weights=` (identical on every rank, e.g. `h2d_weights(device)`) sizes the slabs as `shard_bounds(T, world, weights)`.
     """
 
-    def __init__(self, ua, va, ta, wap, *args, T=None, group=None, comm=None, **kw):
+    def __init__(self, ua, va, ta, wap, *args, T=None, group=None, comm=None, weights=None, **kw):
         from .tem import TEMDiagnostics
         from . import arrays as ar
-        self.group, self.comm = group, comm
+        self.group, self.comm, self.weights = group, comm, weights
         # local number of time steps, before TEMDiagnostics sees the arrays (an empty slab builds nothing)
         r = ar.raw(ua)
         tname = (kw.get('dim_names') or {}).get('time', 'time')
@@ -146,10 +183,10 @@ class ShardedTEM:
                                      self.local.ZM_N if self.local else 0, self.local.ntrac if self.local else 0])
         self.T = int(T) if T is not None else int(meta[:, 0].sum())
         self.K, self.M, self.ntrac = (int(meta[:, j].max()) for j in (1, 2, 3))
-        a, b = shard_bounds(self.T, self._world())[self._rank()]
+        a, b = shard_bounds(self.T, self._world(), self.weights)[self._rank()]
         if b - a != nt_local:
-            raise RuntimeError('rank {} holds {} time steps but shard_bounds({}, {}) assigns it [{}, {})'.format(
-                self._rank(), nt_local, self.T, self._world(), a, b))
+            raise RuntimeError('rank {} holds {} time steps but shard_bounds({}, {}{}) assigns it [{}, {})'.format(
+                self._rank(), nt_local, self.T, self._world(), '' if self.weights is None else ', weights', a, b))
 
     def _allgather_meta(self, vals):
         """[world][len(vals)] integer table, through whichever transport this object uses."""
@@ -191,7 +228,7 @@ class ShardedTEM:
                 blocks.append(self._stack(TRACER_PUBLIC, tracer=i))
                 keys += [(n, i) for n in TRACER_PUBLIC]
         local = torch.cat(blocks, 0) if len(blocks) > 1 else blocks[0]
-        full = gather_time_major(local, self.T, self.group, self.comm)         # [P][T][K][M]
+        full = gather_time_major(local, self.T, self.group, self.comm, self.weights)         # [P][T][K][M]
         out = {}
         for j, (n, i) in enumerate(keys):
             t = full[j] if layout == 'device' else full[j].permute(2, 1, 0)

@@ -19,6 +19,15 @@ def test_shard_bounds():
     assert max(y - x for x, y in b) - min(y - x for x, y in b) == 1
     assert all(b[i][1] == b[i + 1][0] for i in range(7))
     assert shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    # weighted slabs (heterogeneous host links): contiguous, cover [0, T), proportional to the weights
+    w = [23.3] * 4 + [35.4] * 4
+    b = shard_bounds(128, 8, w)
+    assert b[0][0] == 0 and b[-1][1] == 128 and all(b[i][1] == b[i + 1][0] for i in range(7))
+    n = [y - x for x, y in b]
+    assert all(abs(n[i] - 128 * w[i] / sum(w)) <= 1 for i in range(8))
+    assert shard_bounds(10, 2, [1.0, 1.0]) == [(0, 5), (5, 10)]
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, [1.0, -1.0])
 
 
 def _worker(rank, world, port, Ts, q):
@@ -39,7 +48,11 @@ def _gather_case(rank, world, T):
     # the product path: ONE collective for a stack of planes [P][T_local][lev][lat], empty slabs included
     planes = torch.arange(4 * T * 3 * 5, dtype=torch.float64).reshape(4, T, 3, 5)
     got2 = gather_time_major(planes[:, a:b].contiguous(), T)
-    return ok and bool(torch.equal(got2, planes)) and tuple(got2.shape) == (4, T, 3, 5)
+    ok = ok and bool(torch.equal(got2, planes)) and tuple(got2.shape) == (4, T, 3, 5)
+    w = [1.0, 3.0]                                              # weighted slabs: rank 1 owns three quarters
+    a, b = shard_bounds(T, world, w)[rank]
+    got3 = gather_time_major(planes[:, a:b].contiguous(), T, weights=w)
+    return ok and bool(torch.equal(got3, planes))
 
 
 def _run(target, world, *args):

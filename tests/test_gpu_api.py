@@ -345,3 +345,42 @@ def test_several_tracers_pair_kernel(L):
             assert nerr(getattr(both, p_)[i], getattr(alone, p_)[0]) < 1e-11, (i, p_)
     with pytest.raises(RuntimeError, match='qi must be passed'):
         both.etfy()
+
+
+def test_plan_is_reentrant_per_stream():
+    """one split-K workspace per plan made a plan unusable from two streams.  Workspaces are now kept per
+    (plan, stream): the same engine driven from two CUDA streams at once gives the serial results bit for bit."""
+    import torch
+    from pytemdiags_b200.engine import Engine
+    lat, lon = syn.pg2_grid(16)
+    eng = Engine(lat, np.arange(-89.5, 90, 1.0), 60).build_basis()
+    rng = np.random.default_rng(0)
+    xs = [torch.as_tensor(rng.standard_normal((96, lat.shape[0]))).cuda() for _ in range(2)]
+    ref = [eng.project([x]) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for rep in range(5):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                got[i] = eng.project([xs[i]])
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(got[i], ref[i])
+
+
+def test_pageable_staging_is_capped_and_releasable():
+    """the pinned staging buffers for pageable inputs used to live forever on the cached engine."""
+    import pytemdiags_b200
+    from pytemdiags_b200 import TEMDiagnostics, tem as tem_mod
+    lat, lon = syn.pg2_grid(12)
+    K, T = 40, 10                                   # 11 MB per field: above the 8 MB staging threshold
+    plev = syn.default_plev(K)
+    f = syn.synth_fields(lat, lon, plev, T, seed=13)
+    a = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=20, dims=('time', 'lev', 'ncol'), debug_level=0)
+    assert len(tem_mod._HOST_STAGING) > 0
+    pytemdiags_b200.release_host_staging()
+    assert len(tem_mod._HOST_STAGING) == 0
+    b = TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=20, dims=('time', 'lev', 'ncol'), debug_level=0)
+    assert np.array_equal(a.epfy(), b.epfy())
+    pytemdiags_b200.release_host_staging()

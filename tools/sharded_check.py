@@ -42,6 +42,10 @@ for T in ((7, 1) if '--empty' in sys.argv or world > 7 else (7,)):     # 7: unev
         print('rank %d/%d T=%d slab [%d,%d) %s: sharded == unsharded: %s' % (rank, world, T, a, b, transport, good), flush=True)
         ok &= good
     comm.close()
+flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print('ALL %d RANKS OK: %s' % (world, bool(flag.item())), flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
