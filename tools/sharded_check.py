@@ -30,8 +30,11 @@ for T in ((7, 1) if '--empty' in sys.argv or world > 7 else (7,)):     # 7: unev
     ids = [TemdComm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     comm = TemdComm(world, rank, ids[0], dev)
-    for transport, c in (('torch.distributed', None), ('libtemd nccl', comm)):
-        sh = ShardedTEM(f['ua'][a:b], f['va'][a:b], f['ta'][a:b], f['wap'][a:b], plev, lat, q=f['q'][a:b], T=T, comm=c, **kw)
+    wts = [1.0 + (r % 2) for r in range(world)]          # bandwidth-weighted slabs: odd ranks take twice as many steps
+    for transport, c, w in (('torch.distributed', None, None), ('libtemd nccl', comm, None), ('torch.distributed weighted', None, wts)):
+        a, b = shard_bounds(T, world, w)[rank]
+        sh = ShardedTEM(f['ua'][a:b], f['va'][a:b], f['ta'][a:b], f['wap'][a:b], plev, lat, q=f['q'][a:b], T=T, comm=c,
+                        weights=w, **kw)
         out = sh.gather_all()
         good = sh.T == T
         for n in PUBLIC_OUTPUTS:
