@@ -37,8 +37,12 @@ def shard_bounds(T, world, weights=None):
     w = np.asarray(weights, dtype=np.float64)
     if w.shape != (world,) or not np.all(w > 0):
         raise ValueError('weights must be %d positive numbers' % world)
-    edges = np.rint(T * np.concatenate([[0.0], np.cumsum(w)]) / w.sum()).astype(np.int64)
-    edges[-1] = T
+    # minimax apportionment: floor of the proportional share, then the remaining steps one at a time to the rank
+    # whose finishing time (steps + 1) / weight stays smallest - minimises max_r steps_r / weights_r
+    n = np.floor(T * w / w.sum()).astype(np.int64)
+    for _ in range(T - int(n.sum())):
+        n[int(np.argmin((n + 1) / w))] += 1
+    edges = np.concatenate([[0], np.cumsum(n)])
     return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
 
 
@@ -171,7 +175,13 @@ class ShardedTEM:
             dims = kw.get('dims') or ('ncol', 'plev', 'time')[:r.ndim]
         tdim = [i for i, d in enumerate(dims) if d in ('time', tname)]
         nt_local = int(r.shape[tdim[0]]) if tdim else 1
+        import time as _time
+        t_start = _time.perf_counter()
         self.local = TEMDiagnostics(ua, va, ta, wap, *args, **kw) if nt_local > 0 else None
+        # wall time of this rank's own work (upload + kernels; the constructor ends with a synchronising NaN screen):
+        # steps / local_seconds is the rate to feed back into `weights` when slabs should finish together
+        self.local_seconds = _time.perf_counter() - t_start
+        self.local_steps = nt_local
         dev = kw.get('device')
         if self.local is not None:
             dev = self.local.ZM._engine.device

@@ -25,7 +25,9 @@ def test_shard_bounds():
     assert b[0][0] == 0 and b[-1][1] == 128 and all(b[i][1] == b[i + 1][0] for i in range(7))
     n = [y - x for x, y in b]
     assert all(abs(n[i] - 128 * w[i] / sum(w)) <= 1 for i in range(8))
+    assert n == [13, 13, 13, 13, 19, 19, 19, 19]            # minimax: max steps/weight = 13/23.3, not 20/35.4
     assert shard_bounds(10, 2, [1.0, 1.0]) == [(0, 5), (5, 10)]
+    assert shard_bounds(1, 2, [1.0, 2.0]) == [(0, 0), (0, 1)]
     with pytest.raises(ValueError):
         shard_bounds(10, 2, [1.0, -1.0])
 
