@@ -67,7 +67,15 @@ def load():
         except OSError:
             stale = False
         if stale and os.environ.get('TEMD_NO_AUTOBUILD', '0') in ('', '0'):
-            _build.build(force=True)
+            # one builder at a time (torchrun starts N ranks at once): the others wait on the lock and re-check
+            import fcntl
+            with open(os.path.join(_HERE, '.build.lock'), 'w') as lk:
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                try:
+                    if (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < _build._newest_source_mtime():
+                        _build.build(force=True)
+                finally:
+                    fcntl.flock(lk, fcntl.LOCK_UN)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError('libtemd.so not found at %s: run `python -m pytemdiags_b200.build` '
                            '(there is no CPU fallback)' % LIB_PATH)
