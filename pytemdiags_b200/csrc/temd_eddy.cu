@@ -26,7 +26,8 @@
 // (27.0 vs 32.6 TFLOP/s: predicated DMMA + WARPSYNC), run-time selection between loop shapes inside one kernel
 // (ptxas schedules both worse; loop shapes are template parameters instead), splitting GEMM2 over k-steps as
 // well as degrees inside a group (21 accumulator tiles per warp spill under the 120-register cap of 17 warps:
-// 27.9 TFLOP/s), and a look-ahead schedule (GEMM1 of chunk i+1 before GEMM2 of chunk i, group hand-off through an
+// 27.9 TFLOP/s), explicit software pipelining of the GEMM1 fragment loads (two register sets: 80.1 vs 78.5 ms, ptxas'
+// own schedule of the unrolled loop is better), and a look-ahead schedule (GEMM1 of chunk i+1 before GEMM2 of chunk i, group hand-off through an
 // mbarrier waited one phase later so that no warp idles at a barrier: 30.2 TFLOP/s - the barrier is not the limiter).
 #include <cstdlib>
 #include <type_traits>

@@ -37,6 +37,17 @@ def gradient_coefficients(x):
     return coef, uniform, float(dx[0])
 
 
+def _check_rank(lat, L):
+    """Y0 (N x (L+1)) has rank min(L+1, number of distinct latitudes).  The reference's lstsq (gelsd) silently returns
+    the minimum-norm solution when that is < L+1 (sph_zonal_mean.py:389), e.g. the default L=50 on a lat-lon grid with
+    fewer than 51 latitudes; this build refuses, early and with the remedy (documented deviation)."""
+    if L + 1 > 8 and np.unique(lat).shape[0] < L + 1:
+        raise RuntimeError('basis is rank-deficient: L+1 = {} Legendre degrees but only {} distinct latitudes among the {} '
+                           'native columns; lower L to at most {} (the reference would return a minimum-norm '
+                           'least-squares fit here; this build does not)'.format(
+                               L + 1, np.unique(lat).shape[0], lat.shape[0], np.unique(lat).shape[0] - 1))
+
+
 class Engine:
     """One zonal-averaging plan (native grid, output grid, truncation L) on one GPU."""
 
@@ -49,6 +60,7 @@ class Engine:
         self.lat_out = np.ascontiguousarray(np.asarray(lat_out, dtype=np.float64))
         self.N, self.M, self.L = int(self.lat.shape[0]), int(self.lat_out.shape[0]), int(L)
         self.Mld = self.M + (self.M & 1)
+        _check_rank(self.lat, self.L)
         self._plan = C.c_void_p(0)
         _lib.check(self.lib.temd_plan_create(self.device.index or 0, self.N, self.L, self.M, C.byref(self._plan)),
                    'temd_plan_create')
@@ -355,6 +367,8 @@ class DedupEngine(Engine):
         x = np.cos(np.deg2rad(90 - self.lat))
         xu, inv, cnt = np.unique(x, return_inverse=True, return_counts=True)
         self.NU = int(xu.shape[0])
+        if self.NU < self.L + 1:
+            _check_rank(self.lat, self.L)
         self.Uld = self.NU + (self.NU & 1)
         self.multiplicity = self.N / self.NU
         # number the groups by their first column instead of by x: consecutive groups then start at (nearly)

@@ -137,6 +137,12 @@ def test_error_behaviour():
         TEMDiagnostics(f['ua'], f['va'], f['ta'], f['wap'], plev, lat, L=10, dims=('time', 'lev', 'ncol'), debug_level=0, zm_dlat=7)
     with pytest.raises(RuntimeError, match='rank-deficient'):
         sph_zonal_averager(lat, np.arange(-89.5, 90, 1.0), 300).sph_compute_matrices()
+    # the reference's default L=50 on a lat-lon grid with fewer than 51 latitudes is rank-deficient (gelsd
+    # returns a minimum-norm fit there); this build says so, with the remedy, for the dense and the dedup engine
+    lat_ll, _ = syn.latlon_grid(24, 48)
+    for kw in ({}, {'dedup': True}):
+        with pytest.raises(RuntimeError, match='only 24 distinct latitudes.*lower L to at most 23'):
+            sph_zonal_averager(lat_ll, np.arange(-89.5, 90, 1.0), 50, **kw)
     ZM = sph_zonal_averager(lat, np.arange(-89.5, 90, 1.0), 8)
     ZM.sph_compute_matrices()
     with pytest.raises(RuntimeError, match='length'):
