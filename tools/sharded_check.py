@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from pytemdiags_b200 import TEMDiagnostics, synthetic as syn
-from pytemdiags_b200.distributed import PUBLIC_OUTPUTS, TRACER_PUBLIC, ShardedTEM, TemdComm, shard_bounds
+from pytemdiags_b200.distributed import PUBLIC_OUTPUTS, TRACER_PUBLIC, ShardedTEM, TemdComm, h2d_weights, shard_bounds
 
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
@@ -45,6 +45,10 @@ for T in ((7, 1) if '--empty' in sys.argv or world > 7 else (7,)):     # 7: unev
         print('rank %d/%d T=%d slab [%d,%d) %s: sharded == unsharded: %s' % (rank, world, T, a, b, transport, good), flush=True)
         ok &= good
     comm.close()
+hw = h2d_weights(dev, nbytes=64 << 20)                  # per-GPU concurrent H2D GB/s, identical list on every rank
+ok &= len(hw) == world and all(x > 0 for x in hw)
+if rank == 0:
+    print('h2d_weights (GB/s per GPU, all ranks copying at once):', [round(x, 1) for x in hw], flush=True)
 flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
