@@ -13,7 +13,8 @@
 // computing while the other starts or drains.
 //
 // Fused eddy epilogue (field = blockIdx.x / row tiles): out_f = lev_scale * X_f - C_f B, i.e. the native-grid eddy field
-// X' = X - ZM.sph_zonal_mean_native(X) of tem_diagnostics.py:517-529 without a separate element-wise pass.
+// X' = X - ZM.sph_zonal_mean_native(X) of tem_diagnostics.py:517-529 without a separate element-wise pass.  The X tile
+// arrives by TMA through the pipeline stages that the last k-blocks free.
 #include "temd_common.cuh"
 #include "temd_internal.h"
 
@@ -26,8 +27,9 @@ constexpr int SY_STAGE_BYTES = SY_BM * TILE_ROW_BYTES + (SY_BN / 16) * SY_BK * T
 constexpr int SY_STAGES = 4;
 
 struct SynthMaps {
-    CUtensorMap c;   // dims {lpad, rows},  box {16, 128}
-    CUtensorMap b;   // dims {ncol, lpad},  box {16, 16}
+    CUtensorMap c;      // dims {lpad, rows},  box {16, 128}
+    CUtensorMap b;      // dims {ncol, lpad},  box {16, 16}
+    CUtensorMap x[4];   // eddy mode only: the field X_f of this row batch, dims {ncol, rows}, box {16, 128}
 };
 
 // eddy epilogue of field f (x[f] == nullptr: plain synthesis into out[f])
@@ -54,6 +56,7 @@ k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, con
     const int col0 = blockIdx.y * SY_BN;
     const int fld = blockIdx.x / row_tiles;
     const int crow0 = fld * epi.c_field_rows + epi.row_base + row0;   // row coordinate in the coefficient map
+    const bool eddy = (fld == 0 ? epi.x[0] : fld == 1 ? epi.x[1] : fld == 2 ? epi.x[2] : epi.x[3]) != nullptr;
     const uint32_t smem_base = smem_u32(smem), bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (SY_STAGES + s); };
@@ -77,6 +80,19 @@ k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, con
                 for (int b = 0; b < SY_BN / 16; b++)
                     tma_load_2d(dst + SY_BM * TILE_ROW_BYTES + b * SY_BK * TILE_ROW_BYTES, &maps.b, col0 + b * 16,
                                 i * SY_BK, full_bar(s));
+            }
+            if (eddy) {
+                // Eddy mode: the [128 x 64] X tile follows the operands through the ring as four [128 x 16] boxes, one
+                // per stage as the last k-blocks release them: its DRAM latency is hidden under the tail of the main
+                // loop instead of being paid by every thread in the epilogue (ncu r02_prof_syntheddy: 34 % of the warp
+                // samples waiting on those loads, tensor pipe 83 % active against 92 % for the plain synthesis).
+                tma_prefetch_desc(&maps.x[fld]);
+                for (int j = 0; j < SY_BN / 16; j++) {
+                    const int i = nkb + j, s = i % SY_STAGES;
+                    mbar_wait(empty_bar(s), ((i / SY_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(full_bar(s), SY_BM * TILE_ROW_BYTES);
+                    tma_load_2d(smem_base + s * SY_STAGE_BYTES, &maps.x[fld], col0 + j * 16, row0, full_bar(s));
+                }
             }
         }
         return;
@@ -127,22 +143,30 @@ k_synth(const __grid_constant__ SynthMaps maps, int rows, int ncol, int nkb, con
 
     // explicit selects: indexing a kernel-parameter array with a run-time index would copy it to local memory
     double* __restrict__ out = fld == 0 ? epi.out[0] : fld == 1 ? epi.out[1] : fld == 2 ? epi.out[2] : epi.out[3];
-    const double* __restrict__ xin = fld == 0 ? epi.x[0] : fld == 1 ? epi.x[1] : fld == 2 ? epi.x[2] : epi.x[3];
+    if (eddy) {
+        // this warp's 32 columns are X boxes 2 wn and 2 wn + 1 (stages of "k-blocks" nkb + 2 wn, nkb + 2 wn + 1)
+        for (int j = 2 * wn; j < 2 * wn + 2; j++) {
+            const int i = nkb + j;
+            mbar_wait(full_bar(i % SY_STAGES), (i / SY_STAGES) & 1);
+        }
+    }
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
-        const int row = row0 + wm * 32 + mi * 8 + g;
+        const int rl = wm * 32 + mi * 8 + g;          // row inside the tile
+        const int row = row0 + rl;
         if (row >= rows) continue;
         double sc = 1.0;
-        if (xin != nullptr && epi.lev_scale != nullptr && fld == epi.scale_field) sc = epi.lev_scale[(epi.row_base + row) % epi.nlev];
+        if (eddy && epi.lev_scale != nullptr && fld == epi.scale_field) sc = epi.lev_scale[(epi.row_base + row) % epi.nlev];
 #pragma unroll
         for (int jn = 0; jn < 4; jn++) {
             const int col = col0 + wn * 32 + jn * 8 + 2 * t;
             double* dst = out + (size_t)row * ld_out + col;
             double v0 = acc[mi][jn][0], v1 = acc[mi][jn][1];
-            if (xin != nullptr) {
-                const double* xs = xin + (size_t)row * epi.ld_x + col;
-                if (col + 1 < ncol) { const double2 x2 = *reinterpret_cast<const double2*>(xs); v0 = sc * x2.x - v0; v1 = sc * x2.y - v1; }
-                else if (col < ncol) v0 = sc * xs[0] - v0;
+            if (eddy) {
+                const int i = nkb + 2 * wn + (jn >> 1);
+                const double2 x2 = lds128(smem_base + (i % SY_STAGES) * SY_STAGE_BYTES + swz_off(rl, (jn & 1) * 8 + 2 * t));
+                v0 = sc * x2.x - v0;
+                v1 = sc * x2.y - v1;
             }
             if (col + 1 < ncol) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
             else if (col < ncol) *dst = v0;
@@ -160,6 +184,14 @@ static int launch_synth_impl(const double* c, int c_rows_total, int rows, int lp
     for (int f = 0; f < nfields; f++)
         if ((ld_out & 1) || (reinterpret_cast<uintptr_t>(epi.out[f]) & 15))
             return temd_set_error(-1, "synth: output must be 16-byte aligned with an even leading dimension");
+    for (int f = 0; f < 4; f++) {
+        if (f < nfields && epi.x[f] != nullptr) {
+            rc = make_tma_2d(&maps.x[f], epi.x[f], (uint64_t)ncol, (uint64_t)rows, epi.ld_x * sizeof(double), 16, SY_BM);
+            if (rc) return rc;
+        } else {
+            maps.x[f] = maps.b;
+        }
+    }
     constexpr int smem = SY_STAGES * SY_STAGE_BYTES + 1024;
     // per-device attribute: set on every launch (cheap) so that several devices in one process all work
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
