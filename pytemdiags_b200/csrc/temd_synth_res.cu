@@ -7,6 +7,7 @@
 // life and streams [lpad x 16] basis tiles through a TMA/mbarrier ring, writing a [BM x 16] output block per
 // chunk.  Fragment scheme = GEMM1 of k_eddy (MN-major B operand, mnmajor_k permutation, Cs row stride = 4 or
 // 12 mod 16 doubles).  HBM-write-bound for small L (8 B/pt), FP64-tensor-bound for L >~ 25.
+#include <cstdlib>
 #include <type_traits>
 
 #include "temd_common.cuh"
@@ -32,7 +33,7 @@ static inline int sr_ls(int lpad) {
     return ls;
 }
 
-template <int MTW, bool TWO>   // MTW: m8-tiles per warp (2 -> BM = 128, 1 -> BM = 64); TWO: two chunks per iteration
+template <int MTW, int NCHMAX>   // MTW: m8-tiles per warp (2 -> BM = 128, 1 -> BM = 64); NCHMAX: chunks per iteration (1, 2, 4)
 __global__ void __launch_bounds__(SR_THREADS, 1)
 k_synth_res(const __grid_constant__ CUtensorMap qmap, const SynthResParams p) {
     constexpr int BM = SR_WARPS * 8 * MTW;
@@ -148,7 +149,10 @@ k_synth_res(const __grid_constant__ CUtensorMap qmap, const SynthResParams p) {
         }
     };
     int i = 0;
-    if constexpr (TWO) {
+    if constexpr (NCHMAX >= 4) {
+        for (; i + 4 <= nloc; i += 4) round(std::integral_constant<int, 4>{}, i);
+    }
+    if constexpr (NCHMAX >= 2) {
         for (; i + 2 <= nloc; i += 2) round(std::integral_constant<int, 2>{}, i);
     }
     for (; i < nloc; i++) round(std::integral_constant<int, 1>{}, i);
@@ -190,9 +194,14 @@ int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, cons
         if (e != cudaSuccess) return temd_set_error((int)e, "synth_resident: cudaFuncSetAttribute failed");       \
         k_synth_res<M_, T_><<<ntiles * p.nsplit, SR_THREADS, smem, stream>>>(qmap, p);                             \
     } while (0)
-    if (mtw == 2 && nt > 4) SR_LAUNCH(2, true);
-    else if (mtw == 2) SR_LAUNCH(2, false);
-    else SR_LAUNCH(1, true);
+    static const int nch_env = [] { const char* v = getenv("TEMD_SYNTH_RES_NCH"); return v ? atoi(v) : 0; }();
+    int nch = (nt > 4) ? 2 : 1;
+    if (nch_env == 1 || nch_env == 2 || nch_env == 4) nch = nch_env;
+    if (nch == 4 && p.stages < 8) nch = 2;
+    if (mtw == 2 && nch == 4) SR_LAUNCH(2, 4);
+    else if (mtw == 2 && nch == 2) SR_LAUNCH(2, 2);
+    else if (mtw == 2) SR_LAUNCH(2, 1);
+    else SR_LAUNCH(1, 2);
 #undef SR_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess) return temd_set_error((int)e, "synth_resident: kernel launch failed");
