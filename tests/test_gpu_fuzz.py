@@ -63,3 +63,43 @@ def test_random_small_problem(seed):
     if dtype == np.float64:
         for n in ('ub', 'thetab', 'vptpb', 'psi', 'int_vbdp'):
             assert nerr(getattr(tem, n), ref[n]) < 1e-9, (seed, n)
+
+
+@pytest.mark.parametrize('seed', list(range(100, 112)))
+def test_random_grouped_problem_dedup(seed):
+    """Random grids WITH repeated latitudes (random multiplicities 1..50, shuffled columns, random dim order, reversed
+    pressure, float32): the de-duplicated path against the dense CUDA path and the oracle."""
+    from pytemdiags_b200 import TEMDiagnostics
+    rng = np.random.default_rng(seed)
+    U = int(rng.integers(40, 120))
+    mult = rng.integers(1, 51, U) if rng.random() < 0.7 else rng.integers(1, 4, U)
+    lat_u = np.rad2deg(np.arcsin(np.sort(rng.uniform(-0.99, 0.99, U))))
+    lat = np.repeat(lat_u, mult)
+    if rng.random() < 0.7:
+        lat = lat[rng.permutation(lat.shape[0])]
+    N = lat.shape[0]
+    L = int(rng.integers(0, min(30, U // 3) + 1))
+    K, T = int(rng.integers(2, 7)), int(rng.integers(1, 4))
+    plev = np.geomspace(5.0, 1000.0, K) * rng.uniform(0.9, 1.1, K)
+    if rng.random() < 0.5:
+        plev = plev[::-1].copy()
+    shape = (N, K, T)
+    base = {'ta': 210 + 75 * (plev / 1000.0)[None, :, None] ** 0.19 * np.cos(np.deg2rad(lat))[:, None, None] ** 2
+                  + 0.05 * rng.standard_normal(shape),
+            'ua': 20 * rng.standard_normal(shape), 'va': 3 * rng.standard_normal(shape),
+            'wap': 0.05 * rng.standard_normal(shape)}
+    order = list(rng.permutation(3))
+    dims = tuple(('ncol', 'plev', 'time')[i] for i in order)
+    dtype = np.float32 if rng.random() < 0.25 else np.float64
+    fields = {k: np.ascontiguousarray(np.transpose(v, order)).astype(dtype) for k, v in base.items()}
+    ref_in = {k: np.transpose(fields[k].astype(np.float64), np.argsort(order)) for k in base}
+    kw = dict(p=plev, L=L, dims=dims, debug_level=0)
+    dense = TEMDiagnostics(fields['ua'], fields['va'], fields['ta'], fields['wap'], lat, **kw)
+    dd = TEMDiagnostics(fields['ua'], fields['va'], fields['ta'], fields['wap'], lat, dedup=True, **kw)
+    assert dd.ZM._engine.NU == U
+    ref = oracle.tem_suite(ref_in['ua'], ref_in['va'], ref_in['ta'], ref_in['wap'], plev, lat, L=L, literal=False)
+    tol = 2e-5 if dtype == np.float32 else 1e-9
+    for n in oracle.TEM_OUTPUTS:
+        a, b = dd.__getattribute__(n)().astype(np.float64), dense.__getattribute__(n)().astype(np.float64)
+        assert nerr(a, b) < tol, (seed, n, nerr(a, b))
+        assert nerr(a, ref[n]) < 10 * tol, (seed, n, nerr(a, ref[n]))
