@@ -38,7 +38,7 @@
 namespace temd {
 
 constexpr int ED_SMEM_LIMIT = 232448 - 2048;   // 227 KB minus alignment slack and static barriers
-constexpr int ED_MAX_STAGES = 4;
+constexpr int ED_MAX_STAGES = 6;
 
 struct EddyMaps {
     CUtensorMap x[4];   // dims {N, rows}, box {16, BM}
@@ -347,7 +347,18 @@ k_eddy(const __grid_constant__ EddyMaps maps, const EddyParams p) {
     }
 }
 
-static int eddy_bm(int nt) { return nt <= 13 ? 32 : (nt <= 26 ? 16 : 8); }
+// Row tile.  L + 1 <= 104: BM = 32 with 8 (default) / 16 warps and four stages.  TEMD_EDDY_BM=24 selects an
+// experimental layout with 12 consumer warps (three 8-row groups of four warps: every SM sub-partition hosts three
+// warps of three different groups, and the smaller X tiles leave room for FIVE pipeline stages, i.e. 1.5 barrier rounds
+// of TMA look-ahead instead of one).  Measured on the config-2 slab: 80.4 ms against 78.5 ms for 8 fat warps - the
+// four-warps-per-group role split costs more shared-memory traffic than the extra look-ahead returns.
+static int eddy_bm(int nt) {
+    if (nt <= 13) {
+        const char* e = getenv("TEMD_EDDY_BM");      // read per call: A/B in one process
+        return (e && atoi(e) == 24) ? 24 : 32;
+    }
+    return nt <= 26 ? 16 : 8;
+}
 
 int eddy_supported(int lpad) { return lpad >= 8 && lpad / 8 <= 51; }
 
@@ -425,11 +436,11 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
     // subtract in the eddy phase) 8 fat warps (2 fields x 2 n-tiles each, 0.75 LDS per DMMA) beat 16 thin ones at
     // BM = 32: 78.5 vs 82.9 ms (before that change: 80.7 vs 78.6).  BM = 16 keeps 16 warps (only reachable with
     // TEMD_EDDY_MODE=fused: L + 1 > 104 takes the split path); BM = 8 has only 8 GEMM1 units per chunk.
-    int warps = (bm == 16) ? 16 : 8;
-    { const char* e = getenv("TEMD_EDDY_WARPS"); if (e && bm != 8) warps = atoi(e) == 8 ? 8 : 16; }
+    int warps = (bm == 24) ? 12 : (bm == 16) ? 16 : 8;
+    { const char* e = getenv("TEMD_EDDY_WARPS"); if (e && bm != 8 && bm != 24) warps = atoi(e) == 8 ? 8 : 16; }
     rc = -1;
     if (nprod == 4) {
-        if (bm != 32) return temd_set_error(-1, "eddy_flux_project: the tracer-pair kernel serves L + 1 <= 104 (larger L uses the split path)");
+        if (bm != 32) return temd_set_error(-1, "eddy_flux_project: the tracer-pair kernel needs BM = 32 (L + 1 <= 104, TEMD_EDDY_BM unset)");
         p.nch = 1;
         const int nj = (nt + 1) / 2;
         switch (nj) {
@@ -446,7 +457,7 @@ int launch_eddy_flux_project(const double* const* x4, int rows, int ncol, size_t
 #define ED_CASE(BM_, NJ_, W_) if (bm == BM_ && nj == NJ_ && warps == W_) rc = launch_eddy_t<BM_, NJ_, W_>(maps, p, smem, stream);
 #define ED_CASES7(BM_, W_) ED_CASE(BM_, 1, W_) ED_CASE(BM_, 2, W_) ED_CASE(BM_, 3, W_) ED_CASE(BM_, 4, W_) ED_CASE(BM_, 5, W_) ED_CASE(BM_, 6, W_) ED_CASE(BM_, 7, W_)
 #define ED_CASES4(BM_, W_) ED_CASE(BM_, 1, W_) ED_CASE(BM_, 2, W_) ED_CASE(BM_, 3, W_) ED_CASE(BM_, 4, W_)
-    ED_CASES7(32, 8) ED_CASES7(16, 8) ED_CASES7(8, 8) ED_CASES4(32, 16) ED_CASES4(16, 16)
+    ED_CASES7(32, 8) ED_CASES7(16, 8) ED_CASES7(8, 8) ED_CASES4(32, 16) ED_CASES4(16, 16) ED_CASES4(24, 12)
 #undef ED_CASES7
 #undef ED_CASES4
 #undef ED_CASE

@@ -73,6 +73,15 @@ def test_eddy_warp_layouts(monkeypatch, warps):
     test_fused_path_variants(20, 7, 3, 130)
 
 
+def test_eddy_bm24_layout(monkeypatch):
+    """The opt-in BM = 24 / 12-warp / 5-stage layout of k_eddy (TEMD_EDDY_BM=24; measured 80.4 vs 78.5 ms for the
+    default 8-warp BM = 32 layout on the config-2 slab, so it stays an A/B knob)."""
+    monkeypatch.setenv('TEMD_EDDY_BM', '24')
+    monkeypatch.setenv('TEMD_EDDY_MODE', 'fused')
+    for case in ((3, 3, 1, 2), (4, 7, 3, 8), (6, 9, 5, 33), (10, 13, 3, 90), (12, 6, 5, 103)):
+        test_fused_path_variants(*case)
+
+
 @pytest.mark.parametrize('mode', ['fused', 'split'])
 def test_eddy_implementations(monkeypatch, mode):
     """temd_eddy_flux_project has two implementations (fused k_eddy: default for L + 1 <= 104; split k_synth eddy

@@ -44,8 +44,9 @@ for name in (sys.argv[1:] or ['config2', 'config3', 'config4']):
     print('%s rows %d lpad %d: project %.2f ms %.2f TF (%.3f)' % (name, rows, eng.lpad, tp, 8.0 * Lp * N * rows / tp / 1e9,
                                                                  8.0 * Lp * N * rows / tp / 1e9 / PEAK), flush=True)
     ref = None
-    for mode, warps, nch, gb in (('fused', 16, 2, 16), ('fused', 8, 2, 16), ('split', 0, 0, 16), ('split', 0, 0, 40)):
+    for mode, warps, nch, gb in (('fused', 16, 2, 16), ('fused', 8, 2, 16), ('fused', 12, 2, 16), ('split', 0, 0, 16)):
         os.environ['TEMD_EDDY_SCRATCH_GB'] = str(gb)
+        os.environ['TEMD_EDDY_BM'] = '24' if warps == 12 else '32'      # 12 warps = the BM = 24 layout (L + 1 <= 104 only)
         os.environ['TEMD_EDDY_MODE'], os.environ['TEMD_EDDY_WARPS'], os.environ['TEMD_EDDY_NCH'] = mode, str(warps), str(nch)
         try:
             cf = eng.eddy_flux_project(xs[0], xs[1], xs[2], xs[3], c4, lev_scale, K)
@@ -57,7 +58,7 @@ for name in (sys.argv[1:] or ['config2', 'config3', 'config4']):
         ref = cf if ref is None else ref
         tf = 14.0 * Lp * N * rows / te / 1e9
         print('  eddy_flux_project %s warps %2d nch %d scratch %d GB: %.2f ms %.2f TF (%.3f)%s' % (mode, warps, nch, gb, te, tf, tf / PEAK, same), flush=True)
-    for v in ('TEMD_EDDY_MODE', 'TEMD_EDDY_WARPS', 'TEMD_EDDY_NCH', 'TEMD_EDDY_SCRATCH_GB'):
+    for v in ('TEMD_EDDY_MODE', 'TEMD_EDDY_WARPS', 'TEMD_EDDY_NCH', 'TEMD_EDDY_SCRATCH_GB', 'TEMD_EDDY_BM'):
         os.environ.pop(v)
     nat = torch.empty((rows, N + (N & 1)), dtype=torch.float64, device=dev)
     tn = timeit(lambda: eng.synth_native(c4[0], out=nat))
