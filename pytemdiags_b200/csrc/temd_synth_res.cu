@@ -34,7 +34,7 @@ static inline int sr_ls(int lpad) {
 }
 
 template <int MTW, int NCHMAX>   // MTW: m8-tiles per warp (2 -> BM = 128, 1 -> BM = 64); NCHMAX: chunks per iteration (1, 2, 4)
-__global__ void __launch_bounds__(SR_THREADS, 1)
+__global__ void __launch_bounds__(SR_THREADS, MTW == 1 ? 2 : 1)      // BM = 64: two CTAs share an SM
 k_synth_res(const __grid_constant__ CUtensorMap qmap, const SynthResParams p) {
     constexpr int BM = SR_WARPS * 8 * MTW;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -164,7 +164,11 @@ int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, cons
     if (lpad > 104 || ld_c != (size_t)lpad || ncol < 1024) return 0;   // larger L: the generic kernel is faster (measured)
     if ((ld_out & 1) || (reinterpret_cast<uintptr_t>(out) & 15)) return 0;
     const int nt = lpad / 8;
-    const int mtw = (lpad <= 104) ? 2 : 1;
+    // 64-row tiles (MTW = 1) with few enough stages that TWO CTAs share an SM: measured on the config-5 sweep
+    // 0.845 vs 0.822 of the FP64 peak at L = 100, 0.725 vs 0.718 at L = 50, 0.599 vs 0.605 at L = 25
+    // (TEMD_SYNTH_RES_MTW=1|2 forces either).
+    static const int mtw_env = [] { const char* v = getenv("TEMD_SYNTH_RES_MTW"); return v ? atoi(v) : 0; }();
+    const int mtw = (mtw_env == 1 || (mtw_env != 2 && nt > 4)) ? 1 : 2;
     const int bm = SR_WARPS * 8 * mtw;
     SynthResParams p;
     p.rows = rows; p.ncol = ncol;
@@ -177,6 +181,9 @@ int launch_synth_resident(const double* c, int rows, int lpad, size_t ld_c, cons
     const int stage_bytes = lpad * TILE_ROW_BYTES;
     p.stages = (232448 - 2048 - cs_bytes) / stage_bytes;
     if (p.stages > SR_MAX_STAGES) p.stages = SR_MAX_STAGES;
+    if (mtw == 1) {       // keep the CTA under half an SM's shared memory
+        while (p.stages > 2 && p.stages * stage_bytes + cs_bytes + 2048 > 113 * 1024) p.stages--;
+    }
     if (p.stages < 2) return 0;
     const int smem = p.stages * stage_bytes + cs_bytes + 1024;
     const int ntiles = (rows + bm - 1) / bm;
