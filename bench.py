@@ -432,11 +432,15 @@ def e2e_leg(args, ctx, head, xs, plev, lat):
                 tem = TEMDiagnostics(host[0], host[1], host[2], host[3], plev, lat, **kw)
                 return [getattr(tem, n)() for n in PUBLIC]
         else:
+            back = torch.empty((len(PUBLIC), Ttot, K, M), dtype=torch.float64).pin_memory()
+
             def call():
                 sh = ShardedTEM(host[0], host[1], host[2], host[3], plev, lat, T=Ttot, weights=weights, **kw)
                 local_s.append(sh.local_seconds)
-                full = sh.gather_all(tracers=False, layout='device')
-                return [full[n].cpu() for n in PUBLIC]
+                full, _ = sh.gather_all(PUBLIC, tracers=False, layout='stacked')
+                back.copy_(full, non_blocking=True)          # ONE device->host copy of the ten gathered outputs
+                torch.cuda.synchronize()
+                return back
         for _ in range(2):
             call()
         ctx.barrier()

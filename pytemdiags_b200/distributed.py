@@ -231,7 +231,8 @@ class ShardedTEM:
 
     def gather_all(self, names=PUBLIC_OUTPUTS, tracers=True, layout='reference'):
         """One all-gather for every requested output (plus the six tracer diagnostics of every tracer).
-        layout='reference': (lat, plev, time) views like the reference's methods; 'device': [time][lev][lat]."""
+        layout='reference': (lat, plev, time) views like the reference's methods; 'device': [time][lev][lat];
+        'stacked': the tuple (tensor [P][time][lev][lat], [(name, tracer index or None)] * P)."""
         blocks, keys = [self._stack(names)], [(n, None) for n in names]
         if tracers:
             for i in range(self.ntrac):
@@ -239,6 +240,8 @@ class ShardedTEM:
                 keys += [(n, i) for n in TRACER_PUBLIC]
         local = torch.cat(blocks, 0) if len(blocks) > 1 else blocks[0]
         full = gather_time_major(local, self.T, self.group, self.comm, self.weights)         # [P][T][K][M]
+        if layout == 'stacked':      # the gathered block itself (one device->host copy moves everything) + plane keys
+            return full, keys
         out = {}
         for j, (n, i) in enumerate(keys):
             t = full[j] if layout == 'device' else full[j].permute(2, 1, 0)
