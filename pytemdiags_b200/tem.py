@@ -469,8 +469,7 @@ class TEMDiagnostics:
                 consumed = [None, None]
                 side.wait_stream(main)
 
-                def fill(i, t0):
-                    t1 = min(T, t0 + ts)
+                def fill(i, t0, t1):
                     with torch.cuda.stream(side):
                         if consumed[i % 2] is not None:
                             side.wait_event(consumed[i % 2])
@@ -482,14 +481,21 @@ class TEMDiagnostics:
                         for pe in self._pending_stage_events:
                             pe.record(side)       # marks the end of the DMAs that read the pinned staging buffers
                     filled[i % 2] = ev_
-                    return t1
 
-                starts = list(range(0, T, ts))
-                fill(0, starts[0])
-                for i, t0 in enumerate(starts):
-                    t1 = min(T, t0 + ts)
-                    if i + 1 < len(starts):
-                        fill(i + 1, starts[i + 1])
+                # slabs of ts steps, except that the LAST one is halved down to single steps: what is left to do after the
+                # final host->device copy (the path is copy-bound) is then the compute of one step, not of a whole slab
+                slabs = [(t0, min(T, t0 + ts)) for t0 in range(0, T, ts)]
+                if len(slabs) > 1:
+                    t0, t1 = slabs.pop()
+                    while t1 - t0 > 1:
+                        mid = t0 + (t1 - t0 + 1) // 2
+                        slabs.append((t0, mid))
+                        t0 = mid
+                    slabs.append((t0, t1))
+                fill(0, *slabs[0])
+                for i, (t0, t1) in enumerate(slabs):
+                    if i + 1 < len(slabs):
+                        fill(i + 1, *slabs[i + 1])
                     main.wait_event(filled[i % 2])
                     compute([b_[:(t1 - t0) * K, :N] for b_ in bufs[i % 2]], t0, t1)
                     ev_ = torch.cuda.Event()
@@ -525,6 +531,7 @@ class TEMDiagnostics:
         self._dev_results = {n: zm[i] for i, n in enumerate(_ZM_NAMES)}
         self._dev_results.update(res)
         self._cache = {}
+        self._host_public = None
         self._dev_tracer = []
         for i in range(ntr):
             zmq = eng.synth_out(coefq[3 * i:3 * i + 3]).reshape(3, T, K, eng.M)
@@ -539,12 +546,20 @@ class TEMDiagnostics:
         if key in self._cache:
             return self._cache[key]
         src_dict = self._dev_results if tracer is None else self._dev_tracer[tracer]
-        t = src_dict[name].permute(2, 1, 0).contiguous()               # [T][K][M] -> (M, K, T)
         src = self.ua if cast_like is None else cast_like
         dtype = ar.dtype_of(src)
         r = ar.raw(src)
         in_dev = r.device if isinstance(r, torch.Tensor) else None
-        out = ar.from_device(t, 'numpy' if self._kind == 'dataarray' else self._kind, dtype, in_dev)
+        if tracer is None and name in _METHODS and self._kind != 'torch':
+            # host-side outputs of the ten diagnostics methods: ONE device->host copy for all of them on first use
+            # (ten separate permute + copy round trips cost 7 ms of a 244 ms config-2 call, the batch 1.5 ms)
+            if self._host_public is None:
+                blk = torch.stack([self._dev_results[n] for n in _METHODS]).permute(0, 3, 2, 1).contiguous()
+                self._host_public = blk.cpu().numpy()                      # (10, M, K, T)
+            out = self._host_public[_METHODS.index(name)].astype(dtype, copy=False)
+        else:
+            t = src_dict[name].permute(2, 1, 0).contiguous()           # [T][K][M] -> (M, K, T)
+            out = ar.from_device(t, 'numpy' if self._kind == 'dataarray' else self._kind, dtype, in_dev)
         if self._kind == 'dataarray':
             coords = {'lat': self._lat_zm, self.plevname: self.plev, self.timename: self.time}
             out = ar.make_dataarray(self.ua, out, ('lat', self.plevname, self.timename), coords=coords, name=name)
