@@ -40,6 +40,20 @@ def release_host_staging():
     _HOST_STAGING.clear()
 
 
+def _slab_schedule(T, ts):
+    """[(t0, t1)] covering [0, T) in slabs of `ts` time steps whose LAST slab is halved down to single steps
+    (streaming from host memory is copy-bound: the work left after the final copy should be one step, not a slab)."""
+    slabs = [(t0, min(T, t0 + ts)) for t0 in range(0, T, ts)]
+    if len(slabs) > 1:
+        t0, t1 = slabs.pop()
+        while t1 - t0 > 1:
+            mid = t0 + (t1 - t0 + 1) // 2
+            slabs.append((t0, mid))
+            t0 = mid
+        slabs.append((t0, t1))
+    return slabs
+
+
 def _is_1d_of_len(x, n):
     try:
         r = ar.raw(x)
@@ -484,14 +498,7 @@ class TEMDiagnostics:
 
                 # slabs of ts steps, except that the LAST one is halved down to single steps: what is left to do after the
                 # final host->device copy (the path is copy-bound) is then the compute of one step, not of a whole slab
-                slabs = [(t0, min(T, t0 + ts)) for t0 in range(0, T, ts)]
-                if len(slabs) > 1:
-                    t0, t1 = slabs.pop()
-                    while t1 - t0 > 1:
-                        mid = t0 + (t1 - t0 + 1) // 2
-                        slabs.append((t0, mid))
-                        t0 = mid
-                    slabs.append((t0, t1))
+                slabs = _slab_schedule(T, ts)
                 fill(0, *slabs[0])
                 for i, (t0, t1) in enumerate(slabs):
                     if i + 1 < len(slabs):

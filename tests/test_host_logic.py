@@ -157,3 +157,20 @@ def test_format_latlon_data_reference_signature():
     out2 = format_latlon_data(ds2, lat_name='latitude', lon_name='longitude', bnddim_name='bnds')
     assert out2['t'][0] == ('ncol',)
     assert hasattr(PyTEMDiags, 'tem_util') and PyTEMDiags.tem_util.format_latlon_data is format_latlon_data
+
+
+def test_slab_schedule_and_rank_check():
+    """Host helpers of the streaming path: the tapered slab schedule covers the record exactly once, in order; the
+    early rank-deficiency check counts distinct latitudes (default L=50 on a coarse lat-lon grid)."""
+    from pytemdiags_b200.engine import _check_rank
+    for T, ts in ((16, 2), (16, 8), (17, 8), (5, 8), (1, 1), (3, 2), (365, 73), (96, 12)):
+        s = tem_mod._slab_schedule(T, ts)
+        assert s[0][0] == 0 and s[-1][1] == T and all(a[1] == b[0] for a, b in zip(s, s[1:]))
+        assert all(0 < t1 - t0 <= ts for t0, t1 in s)
+        if T > ts:
+            assert s[-1][1] - s[-1][0] == 1                 # the tail after the last copy is one step
+    lat, _ = syn.latlon_grid(24, 48)
+    with pytest.raises(RuntimeError, match='only 24 distinct latitudes'):
+        _check_rank(lat, 50)
+    _check_rank(lat, 23)                                     # L + 1 = 24 <= 24 distinct latitudes: fine
+    _check_rank(lat[:5], 6)                                  # tiny problems (L + 1 <= 8) are left to the factorisation
